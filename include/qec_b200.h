@@ -1,0 +1,105 @@
+/* qec_b200.h -- C ABI of the B200-native QEC-Net quaternion dynamic-routing hot path.
+ *
+ * The reference (tolgabirdal/qecnetworks) has no C ABI: its native code is two
+ * pybind11 modules (models/pytorch-cusolver/torch_cusolver.cpp:558-560,
+ * models/pytorch-autograd-solver/torch_autograd_solver.cpp:267-273) and the rest
+ * of the hot path is ATen ops issued from models/qec_module.py.  These entry
+ * points are what a binding for that path would call; every one cites the
+ * reference interface it replaces.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to contiguous FP32 (int64 / int32 where
+ *    stated) on the current device; quaternions are (w,x,y,z), 16-byte aligned;
+ *  - the caller owns and allocates every buffer; the library never allocates,
+ *    never synchronises and keeps no global mutable state, so it is re-entrant
+ *    (one thread per GPU under DataParallel, one process per GPU under DDP);
+ *  - `stream` is a cudaStream_t (NULL = legacy default stream); all work is
+ *    enqueued on it and is CUDA-graph capturable;
+ *  - return value: 0 on success; -k if the k-th argument is invalid (mirrors
+ *    check_jacobi's "k-th parameter is wrong", torch_cusolver.cpp:162-166);
+ *    a positive cudaError_t if the launch failed.
+ *
+ * Shapes: B batch, P patches, K neighbours, I in_channels, O out_channels,
+ * T routing iterations, BP = B*P, J = K*I votes per output capsule.
+ */
+#ifndef QEC_B200_H
+#define QEC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Library/ABI version (major*100 + minor). */
+int qec_b200_version(void);
+
+/* mean_lrf_per_patch + averageQuaternions + the qrotv of get_votes
+ * (models/qec_module.py:101-110, 35-61, 115-120; models/quat_ops.py:50-68).
+ *   lrfs [BP,K,I,4], act [BP,K,I], points [BP,K,3]
+ *   -> mean [BP,I,4], xrot [BP,K,I,3] (= the input of quater_gen1, i-major xyz-minor).
+ * xrot (and then points) may be NULL to skip the rotation. */
+int qec_lrf_mean_fwd(const float* lrfs, const float* act, const float* points, float* mean, float* xrot, int BP,
+                     int K, int I, void* stream);
+
+/* Backward of the above (autograd through S.symeig in averageQuaternions:
+ * torch_autograd_solver/__init__.py:83-98 -> torch_autograd_solver.cpp:100-169).
+ *   g_xrot [BP,K,I,3], g_mean [BP,I,4] (nullable) -> g_lrfs [BP,K,I,4] (overwritten),
+ *   g_points [BP,K,3] (nullable; ACCUMULATED, caller zero-fills). */
+int qec_lrf_mean_bwd(const float* lrfs, const float* points, const float* mean, const float* g_xrot,
+                     const float* g_mean, float* g_lrfs, float* g_points, int BP, int K, int I, void* stream);
+
+/* get_votes after the two Linears (models/qec_module.py:126-147; quat_ops.qmul :30-48).
+ *   lrfs [BP,K,I,4], t_raw [BP*K, 4*I*O] in the reference feature order q*I*O + i*O + o
+ *   -> votes [BP,O,J,4]. */
+int qec_votes_fwd(const float* lrfs, const float* t_raw, float* votes, int BP, int K, int I, int O, void* stream);
+
+/* Backward: g_votes [BP,O,J,4] -> g_traw [BP*K,4*I*O] (overwritten), g_lrfs [BP,K,I,4]
+ * (nullable; overwritten if O <= 64, otherwise ACCUMULATED: caller zero-fills). */
+int qec_votes_bwd(const float* lrfs, const float* t_raw, const float* g_votes, float* g_traw, float* g_lrfs,
+                  int BP, int K, int I, int O, void* stream);
+
+/* The routing loop + activation of QecModule.forward over materialised votes
+ * (models/qec_module.py:172-194 with mean/weightedAverageQuaternions :149-153, 64-98,
+ * distance :156-160; the S.symeig call at :90 is the in-kernel Jacobi).
+ *   votes [BP,O,J,4], act [BP,J], alpha [1], beta [1]
+ *   -> pose [BP,O,4], agreement [BP,O],
+ *      poses_all [T,BP,O,4] and stats [BP,O,2] (mean inlier score, active-vote count):
+ *      saved for the backward.  1 <= T <= 10. */
+int qec_routing_fwd(const float* votes, const float* act, const float* alpha, const float* beta, float* pose,
+                    float* agreement, float* poses_all, float* stats, int BP, int O, int J, int T, void* stream);
+
+/* Backward through all T iterations (eigenvector adjoint in closed form).
+ *   g_pose [BP,O,4], g_agreement [BP,O]
+ *   -> g_votes [BP,O,J,4] (overwritten),
+ *      g_act [BP,J] (nullable = activation needs no gradient, only the last iteration is
+ *      differentiated; otherwise ACCUMULATED, caller zero-fills),
+ *      g_alpha_beta [2] (ACCUMULATED, caller zero-fills). */
+int qec_routing_bwd(const float* votes, const float* act, const float* alpha, const float* beta,
+                    const float* poses_all, const float* stats, const float* g_pose, const float* g_agreement,
+                    float* g_votes, float* g_act, float* g_alpha_beta, int BP, int O, int J, int T, void* stream);
+
+/* torch_autograd_solver.symeig on [n,4,4] (torch_autograd_solver/__init__.py:141-159,
+ * 74-81 -> torch_cusolver.cpp:194-288): w [n,4] ascending, V [n,4,4] with ROWS =
+ * eigenvectors, upper triangle of the row-major input.
+ * status (nullable): device int, incremented once per matrix that did not converge
+ * (replaces check_jacobi's blocking host loop, torch_cusolver.cpp:150-173). */
+int qec_symeig4_fwd(const float* M, float* w, float* V, int* status, long long n, void* stream);
+
+/* batch_symeig_backward (torch_autograd_solver.cpp:100-169): gw [n,4] and/or gV [n,4,4]
+ * (rows convention; either may be NULL) -> gM [n,4,4].  fold != 0 applies the
+ * reference's final triu(g) + triu(g^T,1). */
+int qec_symeig4_bwd(const float* gw, const float* gV, const float* w, const float* V, float* gM, long long n,
+                    int fold, void* stream);
+
+/* Loader neighbour gather (my_dataloader/modelnet_with_lrf_sample_index_loader.py:130-160).
+ *   point_set [B,N,3], lrf_set [B,N,4], idx [B,P,K] int64 (-1 = empty),
+ *   wrong_ids [B,Wmax] int64 (nullable), wrong_count [B] int32 (nullable = Wmax each)
+ *   -> points [B,P,K,3], lrfs [B,P,K,4], act [B,P,K];
+ *   err: device int set to 1 if an index is out of range (reference: IndexError). */
+int qec_gather(const float* point_set, const float* lrf_set, const long long* idx, const long long* wrong_ids,
+               const int* wrong_count, float* points, float* lrfs, float* act, int* err, int B, int N, int P, int K,
+               int Wmax, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QEC_B200_H */

@@ -1,0 +1,78 @@
+"""ctypes binding of libqec_b200.so (the C ABI declared in include/qec_b200.h).
+
+There is no CPU fallback and no alternative backend: if the library is missing
+the import of any op fails loudly."""
+import ctypes
+import os
+import threading
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libqec_b200.so")
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_LL = ctypes.c_longlong
+
+# name -> (argtypes, kernels launched per call)
+SIGNATURES = {
+    "qec_b200_version": ([], 0),
+    "qec_lrf_mean_fwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _P], 2),
+    "qec_lrf_mean_bwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P], 1),
+    "qec_votes_fwd": ([_P, _P, _P, _I, _I, _I, _I, _P], 1),
+    "qec_votes_bwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _P], 1),
+    "qec_routing_fwd": ([_P] * 8 + [_I, _I, _I, _I, _P], 1),
+    "qec_routing_bwd": ([_P] * 11 + [_I, _I, _I, _I, _P], 1),
+    "qec_symeig4_fwd": ([_P, _P, _P, _P, _LL, _P], 1),
+    "qec_symeig4_bwd": ([_P, _P, _P, _P, _P, _LL, _I, _P], 1),
+    "qec_gather": ([_P] * 9 + [_I, _I, _I, _I, _I, _P], 1),
+}
+
+_lib = None
+_lock = threading.Lock()
+_launches = 0
+
+
+class QecLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library once (thread-safe: DataParallel calls from one thread per GPU)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise QecLibraryError(
+                    "%s not found: build it with `python -m qecnetworks_b200.build` "
+                    "(there is no CPU or PyTorch fallback for the QEC routing kernels)" % LIB_PATH
+                )
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (argtypes, _) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.argtypes = argtypes
+                fn.restype = ctypes.c_int
+            _lib = lib
+    return _lib
+
+
+def call(name, *args):
+    """Invoke an entry point; raise on a non-zero status."""
+    global _launches
+    fn = getattr(load(), name)
+    rc = fn(*args)
+    if rc != 0:
+        if rc < 0:
+            raise QecLibraryError("%s: argument %d is invalid" % (name, -rc))
+        raise QecLibraryError("%s: CUDA error %d at launch" % (name, rc))
+    _launches += SIGNATURES[name][1]
+
+
+def launches():
+    """Number of kernels of this library launched by this process so far."""
+    return _launches
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,251 @@
+// routing.cu -- routing kernels over MATERIALISED votes [B*P, O, J, 4]
+// (the general path; replaces the per-iteration ATen op sequence of reference
+// models/qec_module.py:149-194 and its per-iteration cuSOLVER call).
+//
+// Two launch shapes, chosen by J = K*I votes per capsule:
+//   * group kernel: G lanes of a warp per capsule (G = 1 for small J: the whole
+//     capsule lives in one thread and the Jacobi solves of 32 capsules run in
+//     lock-step across the warp; G = 32 for mid-size J);
+//   * block kernel: one CTA per capsule, votes streamed with coalesced float4
+//     loads, warp-shuffle + shared-memory reduction of the 10 unique entries of
+//     M, solve on warp 0.  The grid is limited to one CTA per SM so that the
+//     capsules in flight (148 x J x 16 B) stay L2-resident between sweeps.
+#include "routing_core.cuh"
+
+namespace qec {
+
+struct VotesCached {  // re-read every sweep: let L1 keep them
+    const float* base;
+    __device__ __forceinline__ Quat get(int j) const { return ldq_nc(base + 4 * (size_t)j); }
+};
+struct VotesStreamed {  // CTA per capsule: too big for L1, stream through L2
+    const float* base;
+    __device__ __forceinline__ Quat get(int j) const { return ldq_stream(base + 4 * (size_t)j); }
+};
+struct SinkGlobal {
+    float* base;
+    __device__ __forceinline__ void put(int j, Quat g) { stq(base + 4 * (size_t)j, g); }
+};
+
+constexpr int kGroupThreads = 128;
+
+template <int G, int TMAX>
+__global__ void __launch_bounds__(kGroupThreads)
+    routing_fwd_group_kernel(const float* __restrict__ votes, const float* __restrict__ act,
+                             const float* __restrict__ alpha_p, const float* __restrict__ beta_p,
+                             float* __restrict__ pose, float* __restrict__ agreement, float* __restrict__ poses_all,
+                             float* __restrict__ stats, long long Nc, int O, int J, int T) {
+    const long long gid = ((long long)blockIdx.x * kGroupThreads + threadIdx.x) / G;
+    const bool active = gid < Nc;
+    const long long c = active ? gid : Nc - 1;  // tail lanes shadow the last capsule (warp-uniform solves)
+    GroupCoop<G> coop;
+    VotesCached vs{votes + (size_t)c * J * 4};
+    const float* act_row = act + (size_t)(c / O) * J;
+    Quat ph[TMAX];
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t) ph[t] = qmake(0.f, 0.f, 0.f, 0.f);
+    float s, n;
+    const float agr = routing_forward_capsule<TMAX>(coop, vs, act_row, J, T, __ldg(alpha_p), __ldg(beta_p), ph, s, n);
+    if (active && coop.leader()) {
+#pragma unroll
+        for (int t = 0; t < TMAX; ++t)
+            if (t < T) {
+                stq(poses_all + ((size_t)t * Nc + c) * 4, ph[t]);
+                if (t == T - 1) stq(pose + (size_t)c * 4, ph[t]);
+            }
+        agreement[c] = agr;
+        stats[2 * c] = s;
+        stats[2 * c + 1] = n;
+    }
+}
+
+template <int BLOCK, int TMAX>
+__global__ void __launch_bounds__(BLOCK)
+    routing_fwd_block_kernel(const float* __restrict__ votes, const float* __restrict__ act,
+                             const float* __restrict__ alpha_p, const float* __restrict__ beta_p,
+                             float* __restrict__ pose, float* __restrict__ agreement, float* __restrict__ poses_all,
+                             float* __restrict__ stats, long long Nc, int O, int J, int T) {
+    __shared__ float scratch[BlockCoop<BLOCK>::kSmemFloats];
+    BlockCoop<BLOCK> coop(scratch);
+    const float alpha = __ldg(alpha_p), beta = __ldg(beta_p);
+    for (long long c = blockIdx.x; c < Nc; c += gridDim.x) {
+        VotesStreamed vs{votes + (size_t)c * J * 4};
+        const float* act_row = act + (size_t)(c / O) * J;
+        Quat ph[TMAX];
+#pragma unroll
+        for (int t = 0; t < TMAX; ++t) ph[t] = qmake(0.f, 0.f, 0.f, 0.f);
+        float s, n;
+        const float agr = routing_forward_capsule<TMAX>(coop, vs, act_row, J, T, alpha, beta, ph, s, n);
+        if (coop.leader()) {
+#pragma unroll
+            for (int t = 0; t < TMAX; ++t)
+                if (t < T) {
+                    stq(poses_all + ((size_t)t * Nc + c) * 4, ph[t]);
+                    if (t == T - 1) stq(pose + (size_t)c * 4, ph[t]);
+                }
+            agreement[c] = agr;
+            stats[2 * c] = s;
+            stats[2 * c + 1] = n;
+        }
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+
+template <int G, int TMAX>
+__global__ void __launch_bounds__(kGroupThreads)
+    routing_bwd_group_kernel(const float* __restrict__ votes, const float* __restrict__ act,
+                             const float* __restrict__ alpha_p, const float* __restrict__ beta_p,
+                             const float* __restrict__ poses_all, const float* __restrict__ stats,
+                             const float* __restrict__ g_pose, const float* __restrict__ g_agr,
+                             float* __restrict__ g_votes, float* g_act, float* g_alpha_beta, long long Nc, int O,
+                             int J, int T) {
+    const long long gid = ((long long)blockIdx.x * kGroupThreads + threadIdx.x) / G;
+    const bool active = gid < Nc;
+    const long long c = active ? gid : Nc - 1;
+    GroupCoop<G> coop;
+    VotesCached vs{votes + (size_t)c * J * 4};
+    // tail lanes recompute the last capsule but must not store: point them at a dead sink
+    SinkGlobal sink{g_votes + (size_t)c * J * 4};
+    const float* act_row = act + (size_t)(c / O) * J;
+    float* g_act_row = (g_act != nullptr && active) ? g_act + (size_t)(c / O) * J : nullptr;
+    Quat ph[TMAX];
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t)
+        ph[t] = (t < T) ? ldq_nc(poses_all + ((size_t)t * Nc + c) * 4) : qmake(0.f, 0.f, 0.f, 0.f);
+    float ga, gb;
+    routing_backward_capsule<TMAX>(coop, vs, sink, act_row, g_act_row, J, T, __ldg(alpha_p), __ldg(beta_p), ph,
+                                   __ldg(stats + 2 * c), __ldg(stats + 2 * c + 1), ldq_nc(g_pose + (size_t)c * 4),
+                                   __ldg(g_agr + c), g_act != nullptr, ga, gb);
+    const bool mine = active && coop.leader();
+    ga = warp_sum(mine ? ga : 0.f);
+    gb = warp_sum(mine ? gb : 0.f);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(g_alpha_beta, ga);
+        atomicAdd(g_alpha_beta + 1, gb);
+    }
+}
+
+template <int BLOCK, int TMAX>
+__global__ void __launch_bounds__(BLOCK)
+    routing_bwd_block_kernel(const float* __restrict__ votes, const float* __restrict__ act,
+                             const float* __restrict__ alpha_p, const float* __restrict__ beta_p,
+                             const float* __restrict__ poses_all, const float* __restrict__ stats,
+                             const float* __restrict__ g_pose, const float* __restrict__ g_agr,
+                             float* __restrict__ g_votes, float* g_act, float* g_alpha_beta, long long Nc, int O,
+                             int J, int T) {
+    __shared__ float scratch[BlockCoop<BLOCK>::kSmemFloats];
+    BlockCoop<BLOCK> coop(scratch);
+    const float alpha = __ldg(alpha_p), beta = __ldg(beta_p);
+    float ga_tot = 0.f, gb_tot = 0.f;
+    for (long long c = blockIdx.x; c < Nc; c += gridDim.x) {
+        VotesStreamed vs{votes + (size_t)c * J * 4};
+        SinkGlobal sink{g_votes + (size_t)c * J * 4};
+        const float* act_row = act + (size_t)(c / O) * J;
+        float* g_act_row = (g_act != nullptr) ? g_act + (size_t)(c / O) * J : nullptr;
+        Quat ph[TMAX];
+#pragma unroll
+        for (int t = 0; t < TMAX; ++t)
+            ph[t] = (t < T) ? ldq_nc(poses_all + ((size_t)t * Nc + c) * 4) : qmake(0.f, 0.f, 0.f, 0.f);
+        float ga, gb;
+        routing_backward_capsule<TMAX>(coop, vs, sink, act_row, g_act_row, J, T, alpha, beta, ph,
+                                       __ldg(stats + 2 * c), __ldg(stats + 2 * c + 1),
+                                       ldq_nc(g_pose + (size_t)c * 4), __ldg(g_agr + c), g_act != nullptr, ga, gb);
+        ga_tot += ga;
+        gb_tot += gb;
+    }
+    if (coop.leader()) {
+        atomicAdd(g_alpha_beta, ga_tot);
+        atomicAdd(g_alpha_beta + 1, gb_tot);
+    }
+}
+
+// group size by votes per capsule
+static inline int pick_group(int J) { return J <= 64 ? 1 : (J <= 2048 ? 32 : 0); }
+constexpr int kBlockThreads = 512;
+
+template <int TMAX>
+static int launch_fwd(const float* votes, const float* act, const float* alpha, const float* beta, float* pose,
+                      float* agreement, float* poses_all, float* stats, long long Nc, int O, int J, int T,
+                      cudaStream_t st) {
+    const int G = pick_group(J);
+    if (G == 1) {
+        const long long blocks = (Nc + kGroupThreads - 1) / kGroupThreads;
+        routing_fwd_group_kernel<1, TMAX><<<(unsigned)blocks, kGroupThreads, 0, st>>>(
+            votes, act, alpha, beta, pose, agreement, poses_all, stats, Nc, O, J, T);
+    } else if (G == 32) {
+        const long long blocks = (Nc * 32 + kGroupThreads - 1) / kGroupThreads;
+        routing_fwd_group_kernel<32, TMAX><<<(unsigned)blocks, kGroupThreads, 0, st>>>(
+            votes, act, alpha, beta, pose, agreement, poses_all, stats, Nc, O, J, T);
+    } else {
+        const long long blocks = Nc < kNumSMs ? Nc : kNumSMs;
+        routing_fwd_block_kernel<kBlockThreads, TMAX><<<(unsigned)blocks, kBlockThreads, 0, st>>>(
+            votes, act, alpha, beta, pose, agreement, poses_all, stats, Nc, O, J, T);
+    }
+    return launch_status();
+}
+
+template <int TMAX>
+static int launch_bwd(const float* votes, const float* act, const float* alpha, const float* beta,
+                      const float* poses_all, const float* stats, const float* g_pose, const float* g_agr,
+                      float* g_votes, float* g_act, float* g_ab, long long Nc, int O, int J, int T,
+                      cudaStream_t st) {
+    const int G = pick_group(J);
+    if (G == 1) {
+        const long long blocks = (Nc + kGroupThreads - 1) / kGroupThreads;
+        routing_bwd_group_kernel<1, TMAX><<<(unsigned)blocks, kGroupThreads, 0, st>>>(
+            votes, act, alpha, beta, poses_all, stats, g_pose, g_agr, g_votes, g_act, g_ab, Nc, O, J, T);
+    } else if (G == 32) {
+        const long long blocks = (Nc * 32 + kGroupThreads - 1) / kGroupThreads;
+        routing_bwd_group_kernel<32, TMAX><<<(unsigned)blocks, kGroupThreads, 0, st>>>(
+            votes, act, alpha, beta, poses_all, stats, g_pose, g_agr, g_votes, g_act, g_ab, Nc, O, J, T);
+    } else {
+        const long long blocks = Nc < kNumSMs ? Nc : kNumSMs;
+        routing_bwd_block_kernel<kBlockThreads, TMAX><<<(unsigned)blocks, kBlockThreads, 0, st>>>(
+            votes, act, alpha, beta, poses_all, stats, g_pose, g_agr, g_votes, g_act, g_ab, Nc, O, J, T);
+    }
+    return launch_status();
+}
+
+}  // namespace qec
+
+using namespace qec;
+
+extern "C" int qec_routing_fwd(const float* votes, const float* act, const float* alpha, const float* beta,
+                               float* pose, float* agreement, float* poses_all, float* stats, int BP, int O, int J,
+                               int T, void* stream) {
+    QEC_CHECK_ARG(votes && act && alpha && beta, 1);
+    QEC_CHECK_ARG(pose && agreement && poses_all && stats, 5);
+    QEC_CHECK_ARG(BP > 0, 9);
+    QEC_CHECK_ARG(O > 0, 10);
+    QEC_CHECK_ARG(J > 0, 11);
+    QEC_CHECK_ARG(T >= 1 && T <= 10, 12);
+    const long long Nc = (long long)BP * O;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (T <= 3) return launch_fwd<3>(votes, act, alpha, beta, pose, agreement, poses_all, stats, Nc, O, J, T, st);
+    return launch_fwd<10>(votes, act, alpha, beta, pose, agreement, poses_all, stats, Nc, O, J, T, st);
+}
+
+extern "C" int qec_routing_bwd(const float* votes, const float* act, const float* alpha, const float* beta,
+                               const float* poses_all, const float* stats, const float* g_pose,
+                               const float* g_agreement, float* g_votes, float* g_act, float* g_alpha_beta, int BP,
+                               int O, int J, int T, void* stream) {
+    QEC_CHECK_ARG(votes && act && alpha && beta && poses_all && stats, 1);
+    QEC_CHECK_ARG(g_pose && g_agreement, 7);
+    QEC_CHECK_ARG(g_votes && g_alpha_beta, 9);
+    QEC_CHECK_ARG(BP > 0, 12);
+    QEC_CHECK_ARG(O > 0, 13);
+    QEC_CHECK_ARG(J > 0, 14);
+    QEC_CHECK_ARG(T >= 1 && T <= 10, 15);
+    const long long Nc = (long long)BP * O;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (T <= 3)
+        return launch_bwd<3>(votes, act, alpha, beta, poses_all, stats, g_pose, g_agreement, g_votes, g_act,
+                             g_alpha_beta, Nc, O, J, T, st);
+    return launch_bwd<10>(votes, act, alpha, beta, poses_all, stats, g_pose, g_agreement, g_votes, g_act,
+                          g_alpha_beta, Nc, O, J, T, st);
+}

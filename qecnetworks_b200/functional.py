@@ -1,0 +1,171 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels (host-side plumbing only:
+PyTorch supplies device memory, the current stream and the autograd graph).
+
+Tensors follow the reference layouts (models/qec_module.py):
+  lrfs [B,P,K,I,4], activation [B,P,K,I], points [B,P,K,3],
+  t_raw [B*P*K, 4*I*O] (feature order q*I*O + i*O + o), votes [B,P,O,K*I,4].
+"""
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check(t, name, shape=None):
+    if not t.is_cuda:
+        raise _lib.QecLibraryError(
+            "%s must be a CUDA tensor: the QEC routing kernels have no CPU implementation" % name
+        )
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32, got %s" % (name, t.dtype))
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError("%s: expected shape %s, got %s" % (name, tuple(shape), tuple(t.shape)))
+    return t.contiguous()
+
+
+class LrfMeanRotate(torch.autograd.Function):
+    """(lrfs, activation, points) -> (mean_lrf [B,P,I,4], xrot [B,P,K,I,3]).
+    reference: QecModule.mean_lrf_per_patch + the qrotv at the top of get_votes
+    (qec_module.py:101-120)."""
+
+    @staticmethod
+    def forward(ctx, lrfs, activation, points):
+        B, P, K, I, _ = lrfs.shape
+        lrfs = _check(lrfs, "lrfs", (B, P, K, I, 4))
+        activation = _check(activation, "activation", (B, P, K, I))
+        points = _check(points, "points", (B, P, K, 3))
+        mean = torch.empty(B, P, I, 4, device=lrfs.device, dtype=torch.float32)
+        xrot = torch.empty(B, P, K, I, 3, device=lrfs.device, dtype=torch.float32)
+        call("qec_lrf_mean_fwd", ptr(lrfs), ptr(activation), ptr(points), ptr(mean), ptr(xrot), B * P, K, I, _stream())
+        ctx.save_for_backward(lrfs, points, mean)
+        return mean, xrot
+
+    @staticmethod
+    def backward(ctx, g_mean, g_xrot):
+        lrfs, points, mean = ctx.saved_tensors
+        B, P, K, I, _ = lrfs.shape
+        need_lrfs, _, need_points = ctx.needs_input_grad
+        if g_xrot is None:
+            g_xrot = torch.zeros(B, P, K, I, 3, device=lrfs.device, dtype=torch.float32)
+        g_xrot = g_xrot.contiguous()
+        g_mean = None if g_mean is None else g_mean.contiguous()
+        g_lrfs = torch.empty_like(lrfs)
+        g_points = torch.zeros_like(points) if need_points else None
+        call("qec_lrf_mean_bwd", ptr(lrfs), ptr(points), ptr(mean), ptr(g_xrot), ptr(g_mean), ptr(g_lrfs),
+             ptr(g_points), B * P, K, I, _stream())
+        return (g_lrfs if need_lrfs else None), None, g_points
+
+
+class Votes(torch.autograd.Function):
+    """(lrfs [B,P,K,I,4], t_raw [B*P*K, 4*I*O]) -> votes [B,P,O,K*I,4].
+    reference: QecModule.get_votes after the Linears (qec_module.py:126-147)."""
+
+    @staticmethod
+    def forward(ctx, lrfs, t_raw):
+        B, P, K, I, _ = lrfs.shape
+        O = t_raw.shape[-1] // (4 * I)
+        lrfs = _check(lrfs, "lrfs", (B, P, K, I, 4))
+        t_raw = _check(t_raw, "t_raw", (B * P * K, 4 * I * O))
+        votes = torch.empty(B, P, O, K * I, 4, device=lrfs.device, dtype=torch.float32)
+        call("qec_votes_fwd", ptr(lrfs), ptr(t_raw), ptr(votes), B * P, K, I, O, _stream())
+        ctx.save_for_backward(lrfs, t_raw)
+        return votes
+
+    @staticmethod
+    def backward(ctx, g_votes):
+        lrfs, t_raw = ctx.saved_tensors
+        B, P, K, I, _ = lrfs.shape
+        O = t_raw.shape[-1] // (4 * I)
+        need_lrfs = ctx.needs_input_grad[0]
+        g_votes = g_votes.contiguous()
+        g_traw = torch.empty_like(t_raw)
+        g_lrfs = torch.zeros_like(lrfs) if need_lrfs else None
+        call("qec_votes_bwd", ptr(lrfs), ptr(t_raw), ptr(g_votes), ptr(g_traw), ptr(g_lrfs), B * P, K, I, O, _stream())
+        return g_lrfs, g_traw
+
+
+class Routing(torch.autograd.Function):
+    """(votes [B,P,O,J,4], activation [B,P,J], alpha [1], beta [1], T) -> (pose [B,P,O,4],
+    agreement [B,P,O]).  reference: the loop and epilogue of QecModule.forward
+    (qec_module.py:172-194)."""
+
+    @staticmethod
+    def forward(ctx, votes, activation, alpha, beta, num_iterations):
+        B, P, O, J, _ = votes.shape
+        votes = _check(votes, "votes", (B, P, O, J, 4))
+        activation = _check(activation, "activation", (B, P, J))
+        alpha = _check(alpha, "alpha", (1,))
+        beta = _check(beta, "beta", (1,))
+        T = int(num_iterations)
+        dev = votes.device
+        pose = torch.empty(B, P, O, 4, device=dev, dtype=torch.float32)
+        agreement = torch.empty(B, P, O, device=dev, dtype=torch.float32)
+        poses_all = torch.empty(T, B, P, O, 4, device=dev, dtype=torch.float32)
+        stats = torch.empty(B, P, O, 2, device=dev, dtype=torch.float32)
+        call("qec_routing_fwd", ptr(votes), ptr(activation), ptr(alpha), ptr(beta), ptr(pose), ptr(agreement),
+             ptr(poses_all), ptr(stats), B * P, O, J, T, _stream())
+        ctx.save_for_backward(votes, activation, alpha, beta, poses_all, stats)
+        ctx.T = T
+        return pose, agreement
+
+    @staticmethod
+    def backward(ctx, g_pose, g_agreement):
+        votes, activation, alpha, beta, poses_all, stats = ctx.saved_tensors
+        B, P, O, J, _ = votes.shape
+        dev = votes.device
+        g_pose = torch.zeros(B, P, O, 4, device=dev) if g_pose is None else g_pose.contiguous()
+        g_agreement = torch.zeros(B, P, O, device=dev) if g_agreement is None else g_agreement.contiguous()
+        need_act = ctx.needs_input_grad[1]
+        g_votes = torch.empty_like(votes)
+        g_act = torch.zeros_like(activation) if need_act else None
+        g_ab = torch.zeros(2, device=dev, dtype=torch.float32)
+        call("qec_routing_bwd", ptr(votes), ptr(activation), ptr(alpha), ptr(beta), ptr(poses_all), ptr(stats),
+             ptr(g_pose), ptr(g_agreement), ptr(g_votes), ptr(g_act), ptr(g_ab), B * P, O, J, ctx.T, _stream())
+        return g_votes, g_act, g_ab[0:1], g_ab[1:2], None
+
+
+def lrf_mean_rotate(lrfs, activation, points):
+    return LrfMeanRotate.apply(lrfs, activation, points)
+
+
+def votes(lrfs, t_raw):
+    return Votes.apply(lrfs, t_raw)
+
+
+def routing(votes_, activation, alpha, beta, num_iterations):
+    return Routing.apply(votes_, activation, alpha, beta, num_iterations)
+
+
+def neighbour_gather(point_set, lrf_set, idx, wrong_ids=None, wrong_count=None):
+    """Batched loader gather on the device (reference
+    my_dataloader/modelnet_with_lrf_sample_index_loader.py:130-160).
+    point_set [B,N,3], lrf_set [B,N,4], idx [B,P,K] int64, wrong_ids [B,W] int64.
+    Returns points [B,P,K,3], lrfs [B,P,K,4], act [B,P,K].  Raises IndexError on an
+    out-of-range index like the reference's tensor indexing would."""
+    B, N, _ = point_set.shape
+    _, P, K = idx.shape
+    point_set = _check(point_set, "point_set", (B, N, 3))
+    lrf_set = _check(lrf_set, "lrf_set", (B, N, 4))
+    if not idx.is_cuda or idx.dtype != torch.int64:
+        raise TypeError("idx must be a CUDA int64 tensor")
+    idx = idx.contiguous()
+    W = 0
+    if wrong_ids is not None:
+        wrong_ids = wrong_ids.to(device=idx.device, dtype=torch.int64).contiguous().view(B, -1)
+        W = wrong_ids.shape[1]
+        if W == 0:
+            wrong_ids = None
+    if wrong_count is not None:
+        wrong_count = wrong_count.to(device=idx.device, dtype=torch.int32).contiguous()
+    dev = idx.device
+    points = torch.empty(B, P, K, 3, device=dev, dtype=torch.float32)
+    lrfs = torch.empty(B, P, K, 4, device=dev, dtype=torch.float32)
+    act = torch.empty(B, P, K, device=dev, dtype=torch.float32)
+    err = torch.zeros(1, device=dev, dtype=torch.int32)
+    call("qec_gather", ptr(point_set), ptr(lrf_set), ptr(idx), ptr(wrong_ids), ptr(wrong_count), ptr(points),
+         ptr(lrfs), ptr(act), ptr(err), B, N, P, K, W, _stream())
+    return points, lrfs, act, err

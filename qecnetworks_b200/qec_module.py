@@ -1,0 +1,57 @@
+"""QecModule -- drop-in for the reference routing layer (models/qec_module.py:11-194).
+
+Same constructor, parameters, state_dict keys/shapes and forward signature; the
+forward is the B200 kernel pipeline instead of the ATen op sequence:
+
+    lrf_mean_rotate  (1 launch pair)   mean LRF per patch + point rotation
+    quater_gen1/2    (cuBLAS SGEMM)    the two Linears stay dense library GEMMs
+    votes            (1 launch)        normalise + fix + Hamilton + fix + transpose
+    routing          (1 launch)        all T IRLS iterations + activation, fused
+
+No host synchronisation anywhere (the reference syncs 2(1+T) times per forward:
+nonzero() and cuSOLVER's info copy).
+"""
+import torch
+from torch.nn import Linear, Module, Parameter
+
+from . import functional as QF
+
+
+class QecModule(Module):
+    def __init__(self, in_channels, out_channels, num_iterations=3, num_neighbours=8, num_patches=8):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.num_iterations = num_iterations
+        self.num_neighbours = num_neighbours
+        self.num_patches = num_patches
+        self.bottle_neck = in_channels * out_channels
+
+        self.quater_gen1 = Linear(3 * in_channels, out_channels, bias=True)
+        self.quater_gen2 = Linear(out_channels, out_channels * in_channels * 4, bias=True)
+        self.alpha = Parameter(torch.ones(1))
+        self.beta = Parameter(torch.ones(1))
+
+    def reset_parameters(self):
+        self.alpha.data.fill_(1)
+        self.beta.data.fill_(1)
+
+    def forward(self, points, lrfs, activation):
+        """points [B,P,K,3], lrfs [B,P,K,I,4], activation [B,P,K,I]
+        -> pose [B,P,O,4] (O squeezed when 1, as the reference's pose.squeeze(-2)),
+           agreement [B,P,O]."""
+        B, P, K, I, _ = lrfs.shape
+        O = self.out_channels
+        if I != self.in_channels or K != self.num_neighbours or P != self.num_patches:
+            raise ValueError(
+                "QecModule(in=%d, K=%d, P=%d) got lrfs %s"
+                % (self.in_channels, self.num_neighbours, self.num_patches, tuple(lrfs.shape))
+            )
+        points = points.float().contiguous()
+        lrfs = lrfs.float().contiguous()
+        activation = activation.float().contiguous()
+        _, xrot = QF.lrf_mean_rotate(lrfs, activation, points)
+        t_raw = self.quater_gen2(self.quater_gen1(xrot.view(B * P * K, 3 * I)))
+        votes = QF.votes(lrfs, t_raw)
+        pose, agreement = QF.routing(votes, activation.view(B, P, K * I), self.alpha, self.beta, self.num_iterations)
+        return pose.squeeze(-2), agreement

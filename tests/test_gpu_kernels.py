@@ -1,0 +1,244 @@
+"""GPU parity tests, kernel by kernel: every C-ABI entry point against the CPU oracle
+on the same seeded inputs (run on the B200 box: pytest -m gpu).
+
+Tolerance: BASELINE.json north_star -- 1e-4 in fp32, quaternions compared up to sign,
+gradients under the same tolerance (relative to the largest reference magnitude)."""
+import pytest
+import torch
+
+from oracle import qec_oracle as orc
+from tests.util import load_golden, quat_err, max_err, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def cuda():
+    if not torch.cuda.is_available():
+        pytest.fail("CUDA device required for -m gpu tests")
+    return torch.device("cuda:0")
+
+
+def clustered(shape, g, spread=0.3):
+    base = torch.randn(shape[0], *([1] * (len(shape) - 1)), 4, generator=g, dtype=torch.float64)
+    q = base + spread * torch.randn(*shape, 4, generator=g, dtype=torch.float64)
+    q = q / q.norm(dim=-1, keepdim=True)
+    return (q * torch.where(q[..., :1] < 0, -1.0, 1.0)).float()
+
+
+# ---------------------------------------------------------------- symeig (L0 boundary)
+def test_symeig_forward_golden():
+    import qecnetworks_b200 as qb
+
+    dev = cuda()
+    g = load_golden("symeig")
+    w, V = qb.symeig(g["cov"].to(dev))
+    w, V = w.cpu(), V.cpu()
+    assert max_err(w, g["w"]) < 1e-5
+    rec = V.transpose(1, 2) @ torch.diag_embed(w) @ V  # rows are eigenvectors
+    assert max_err(rec, g["cov"]) < 1e-5
+    assert quat_err(orc.fix(V[:, 3]), g["top"]) < 1e-5
+    assert max_err(V @ V.transpose(1, 2), torch.eye(4).expand(80, 4, 4)) < 1e-5
+    wb, Vb = qb.symeig(g["bug"].unsqueeze(0).to(dev))
+    assert max_err(wb.cpu(), g["bug_w"]) < 1e-5
+
+
+def test_symeig_top_gradient_golden():
+    """the reference's only live backward test (pytorch-autograd-solver/test.py:101-141)"""
+    import qecnetworks_b200 as qb
+
+    dev = cuda()
+    g = load_golden("symeig")
+    x = g["x"].to(dev).requires_grad_(True)
+    q = x / x.norm(dim=-1, keepdim=True)
+    cov = torch.einsum("nkc,nkd->ncd", q, q)
+    _, V = qb.symeig(cov)
+    top = V[:, 3]
+    (top * torch.sign(top[:, :1])).mean().backward()
+    assert rel_err(x.grad.cpu(), g["grad_x"]) < TOL
+
+
+def test_symeig_backward_vs_oracle():
+    import qecnetworks_b200 as qb
+
+    dev = cuda()
+    gen = torch.Generator().manual_seed(5)
+    A = torch.randn(257, 4, 4, generator=gen)
+    A = A @ A.transpose(1, 2)
+    w, V = orc.symeig_rows(A.double())
+    gw = torch.randn(257, 4, generator=gen)
+    gV = torch.randn(257, 4, 4, generator=gen)
+    ref = orc.symeig_rows_backward(gw.double(), gV.double(), w, V)
+    Ad = A.to(dev).requires_grad_(True)
+    wd, Vd = qb.symeig(Ad, fold=False)
+    # eigenvector signs are arbitrary: feed a sign-consistent cotangent
+    sgn = torch.sign((Vd.detach().cpu().double() * V).sum(-1, keepdim=True))
+    torch.autograd.backward([wd, Vd], [gw.to(dev), (gV * sgn.float()).to(dev)])
+    assert rel_err(Ad.grad.cpu(), ref) < 1e-3  # F = 1/(w_j - w_i) amplifies fp32 rounding on random spectra
+    # folded variant: triu(g) + triu(g^T, 1)
+    Af = A.to(dev).requires_grad_(True)
+    wf, Vf = qb.symeig(Af, fold=True)
+    torch.autograd.backward([wf, Vf], [gw.to(dev), (gV * sgn.float()).to(dev)])
+    folded = torch.triu(ref) + torch.triu(ref.transpose(1, 2), 1)
+    assert rel_err(Af.grad.cpu(), folded) < 1e-3
+
+
+# ---------------------------------------------------------------- LRF mean + rotation
+@pytest.mark.parametrize("B,P,K,I", [(2, 3, 5, 4), (3, 16, 9, 1), (2, 1, 256, 8), (1, 2, 40, 33)])
+def test_lrf_mean_rotate(B, P, K, I):
+    from qecnetworks_b200 import functional as QF
+
+    dev = cuda()
+    gen = torch.Generator().manual_seed(B * 1000 + K)
+    lrfs = clustered((B, P, K, I), gen)
+    act = (torch.rand(B, P, K, I, generator=gen) < 0.8).float()
+    act[0, 0, :, 0] = 0  # a channel with no active neighbour -> zero mean
+    lrfs = lrfs * (torch.rand(B, P, K, I, 1, generator=gen) < 0.9)
+    points = torch.randn(B, P, K, 3, generator=gen)
+    G = torch.randn(B, P, K, I, 3, generator=gen)
+
+    l64 = lrfs.double().requires_grad_(True)
+    p64 = points.double().requires_grad_(True)
+    mean_ref = orc.lrf_mean(l64, act.double())
+    x_ref = orc.rotate_points(mean_ref, p64)
+    (x_ref * G.double()).sum().backward()
+
+    ld = lrfs.to(dev).requires_grad_(True)
+    pd = points.to(dev).requires_grad_(True)
+    mean, xrot = QF.lrf_mean_rotate(ld, act.to(dev), pd)
+    assert quat_err(mean.cpu(), mean_ref) < TOL
+    assert float(mean[0, 0, 0].abs().max()) == 0.0
+    assert max_err(xrot.cpu(), x_ref) < TOL
+    (xrot * G.to(dev)).sum().backward()
+    assert rel_err(ld.grad.cpu(), l64.grad) < TOL
+    assert rel_err(pd.grad.cpu(), p64.grad) < TOL
+
+
+# ---------------------------------------------------------------- votes
+@pytest.mark.parametrize("B,P,K,I,O", [(2, 3, 5, 4, 6), (2, 8, 9, 1, 128), (1, 1, 40, 16, 40), (1, 2, 3, 70, 65)])
+def test_votes(B, P, K, I, O):
+    from qecnetworks_b200 import functional as QF
+
+    dev = cuda()
+    gen = torch.Generator().manual_seed(K * 100 + O)
+    lrfs = clustered((B, P, K, I), gen)
+    lrfs[0, 0, 0] = 0
+    t_raw = torch.randn(B * P * K, 4 * I * O, generator=gen)
+    t_raw[0, :O] = 0.0  # w == 0 -> sign(0) = 0 zeroes the transform
+    G = torch.randn(B, P, O, K * I, 4, generator=gen)
+
+    l64 = lrfs.double().requires_grad_(True)
+    t64 = t_raw.double().requires_grad_(True)
+    v_ref = orc.votes_from(l64, t64.view(B, P, K, 4, I, O))
+    (v_ref * G.double()).sum().backward()
+
+    ld = lrfs.to(dev).requires_grad_(True)
+    td = t_raw.to(dev).requires_grad_(True)
+    v = QF.votes(ld, td)
+    assert max_err(v.cpu(), v_ref) < 1e-5
+    (v * G.to(dev)).sum().backward()
+    assert rel_err(td.grad.cpu(), t64.grad) < TOL
+    assert rel_err(ld.grad.cpu(), l64.grad) < TOL
+
+
+# ---------------------------------------------------------------- routing
+def _routing_case(B, P, O, J, T, frac, seed, need_act=True):
+    from qecnetworks_b200 import functional as QF
+
+    dev = cuda()
+    gen = torch.Generator().manual_seed(seed)
+    votes = clustered((B, P, O, J), gen, spread=0.35)
+    if frac:
+        act = torch.rand(B, P, J, generator=gen) * 0.6 + 0.3
+    else:
+        act = torch.ones(B, P, J)
+    act = act * (torch.rand(B, P, J, generator=gen) < 0.85)
+    act[:, :, 0] = 1.0
+    votes[0, 0, :, min(1, J - 1)] = 0  # a zero vote (inactive neighbour's zero LRF)
+    if B * P > 1:
+        votes[-1, -1, 0] = 0  # a capsule with no votes at all -> pose 0
+        act[-1, -1, :] = act[-1, -1, :]
+    alpha = torch.tensor([1.3])
+    beta = torch.tensor([0.7])
+    Gp = torch.randn(B, P, O, 4, generator=gen)
+    Ga = torch.randn(B, P, O, generator=gen)
+
+    v64 = votes.double().requires_grad_(True)
+    a64 = act.double().requires_grad_(need_act)
+    al64 = alpha.double().requires_grad_(True)
+    be64 = beta.double().requires_grad_(True)
+    pose_ref, agr_ref, poses_ref = orc.routing(v64, a64, al64, be64, T, return_all=True)
+    ((pose_ref * Gp.double()).sum() + (agr_ref * Ga.double()).sum()).backward()
+
+    vd = votes.to(dev).requires_grad_(True)
+    ad = act.to(dev).requires_grad_(need_act)
+    ald = alpha.to(dev).requires_grad_(True)
+    bed = beta.to(dev).requires_grad_(True)
+    pose, agr = QF.routing(vd, ad, ald, bed, T)
+    assert quat_err(pose.cpu(), pose_ref) < TOL
+    assert max_err(agr.cpu(), agr_ref) < TOL
+    if B * P > 1:
+        assert float(pose[-1, -1, 0].abs().max()) == 0.0
+    ((pose * Gp.to(dev)).sum() + (agr * Ga.to(dev)).sum()).backward()
+    assert rel_err(vd.grad.cpu(), v64.grad) < TOL
+    if need_act:
+        assert rel_err(ad.grad.cpu(), a64.grad) < TOL
+    assert rel_err(ald.grad.cpu(), al64.grad) < TOL
+    assert rel_err(bed.grad.cpu(), be64.grad) < TOL
+
+
+@pytest.mark.parametrize(
+    "B,P,O,J,T,frac",
+    [
+        (2, 3, 6, 20, 3, True),      # thread per capsule
+        (2, 8, 16, 9, 3, False),     # pool1-like
+        (2, 2, 5, 9, 1, True),       # T = 1
+        (2, 2, 5, 9, 2, True),       # T = 2
+        (1, 2, 7, 64, 3, True),      # largest thread-per-capsule J
+        (2, 2, 3, 300, 3, True),     # warp per capsule
+        (1, 2, 3, 2048, 3, True),    # largest warp-per-capsule J
+        (1, 2, 5, 4100, 3, True),    # CTA per capsule, ragged tail
+        (1, 1, 3, 100, 5, True),     # T > 3 instantiation
+    ],
+)
+def test_routing(B, P, O, J, T, frac):
+    _routing_case(B, P, O, J, T, frac, seed=J * 10 + T)
+
+
+def test_routing_no_activation_grad():
+    _routing_case(2, 4, 8, 9, 3, False, seed=77, need_act=False)
+    _routing_case(1, 1, 4, 3000, 3, True, seed=78, need_act=False)
+
+
+def test_routing_pool2_shape():
+    """pool2 geometry of BASELINE config 2 at B=1: 40 capsules x 32768 votes"""
+    _routing_case(1, 1, 40, 32768, 3, True, seed=79)
+
+
+# ---------------------------------------------------------------- gather (row d)
+def test_gather_bit_exact():
+    from qecnetworks_b200 import functional as QF
+
+    dev = cuda()
+    gen = torch.Generator().manual_seed(9)
+    B, N, P, K = 3, 500, 256, 9
+    ps = torch.randn(B, N, 3, generator=gen)
+    ls = torch.randn(B, N, 4, generator=gen)
+    idx = torch.randint(0, N, (B, P, K), generator=gen)
+    idx[:, 200:, :] = -1
+    idx[:, :, 5:][torch.rand(B, P, 4, generator=gen) < 0.3] = -1
+    idx[0, 3, 2] = 0          # id 0: act 0 but a live LRF
+    idx[1, 7, 1] = N - 1      # the zeroed last row
+    wrong = torch.stack([idx[b, :50].reshape(-1)[torch.randperm(450, generator=gen)[:6]] for b in range(B)])
+    points, lrfs, act, err = QF.neighbour_gather(ps.to(dev), ls.to(dev), idx.to(dev), wrong.to(dev))
+    assert int(err.item()) == 0
+    for b in range(B):
+        w = wrong[b][wrong[b] > 0]
+        rp, rl, ra = orc.neighbour_gather(ps[b], ls[b], idx[b], wrong[b])
+        assert torch.equal(points[b].cpu(), rp)
+        assert torch.equal(lrfs[b].cpu(), rl)
+        assert torch.equal(act[b].cpu(), ra)
+    bad = idx.clone()
+    bad[0, 0, 0] = N + 3
+    _, _, _, err = QF.neighbour_gather(ps.to(dev), ls.to(dev), bad.to(dev))
+    assert int(err.item()) == 1

@@ -1,0 +1,155 @@
+"""GPU parity of the drop-in QecModule / QecNet / QecSiaNet against the golden vectors
+of the unmodified reference and against the CPU oracle (pytest -m gpu)."""
+import pytest
+import torch
+
+from oracle import qec_oracle as orc
+from tests.util import load_golden, params_of, quat_err, max_err, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def cuda():
+    if not torch.cuda.is_available():
+        pytest.fail("CUDA device required for -m gpu tests")
+    return torch.device("cuda:0")
+
+
+def make_module(g, dev):
+    import qecnetworks_b200 as qb
+
+    B, P, K, I, O, T = [int(v) for v in g["dims"]]
+    mod = qb.QecModule(I, O, num_iterations=T, num_neighbours=K, num_patches=P)
+    mod.load_state_dict(params_of(g), strict=True)  # the reference's own keys and shapes
+    return mod.to(dev)
+
+
+CASES = ["module_small", "module_pool1like", "module_T1", "module_T2", "module_O1"]
+
+
+@pytest.mark.parametrize("name", CASES + ["module_cfg1_B2"])
+def test_module_forward_golden(name):
+    dev = cuda()
+    g = load_golden(name)
+    mod = make_module(g, dev)
+    with torch.no_grad():
+        pose, agr = mod(g["points"].to(dev), g["lrfs"].to(dev), g["act"].to(dev))
+    assert pose.shape == g["pose"].shape and agr.shape == g["agreement"].shape
+    assert quat_err(pose.cpu(), g["pose"]) < TOL
+    assert max_err(agr.cpu(), g["agreement"]) < TOL
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_module_backward_golden(name):
+    dev = cuda()
+    g = load_golden(name)
+    mod = make_module(g, dev)
+    points = g["points"].to(dev).requires_grad_(True)
+    lrfs = g["lrfs"].to(dev).requires_grad_(True)
+    act = g["act"].to(dev).requires_grad_(True)
+    pose, agr = mod(points, lrfs, act)
+    ((pose * g["cot.pose"].to(dev)).sum() + (agr * g["cot.agreement"].to(dev)).sum()).backward()
+    assert rel_err(points.grad.cpu(), g["grad.points"]) < TOL
+    assert rel_err(lrfs.grad.cpu(), g["grad.lrfs"]) < TOL
+    assert rel_err(act.grad.cpu(), g["grad.act"]) < TOL
+    for k, v in mod.named_parameters():
+        assert rel_err(v.grad.cpu(), g["grad." + k]) < TOL, k
+
+
+def _net(g, dev, sia):
+    import qecnetworks_b200 as qb
+
+    B, C, ncls, T = [int(v) for v in g["dims"]]
+    net = (qb.QecSiaNet if sia else qb.QecNet)(2048, C, ncls, T)
+    net.load_state_dict(params_of(g), strict=True)
+    return net.to(dev)
+
+
+def test_net_golden():
+    dev = cuda()
+    g = load_golden("net_small")
+    net = _net(g, dev, False)
+    pose, a = net(g["points"].to(dev), g["lrfs"].to(dev), g["act"].to(dev), None)
+    assert quat_err(pose.cpu(), g["pose"]) < TOL
+    assert max_err(a.cpu(), g["agreement"]) < TOL
+    loss = net.spread_loss(a, g["labels"].to(dev), 0)
+    assert abs(float(loss) - float(g["loss"])) < 1e-5
+    loss.backward()
+    for k, v in net.named_parameters():
+        assert rel_err(v.grad.cpu(), g["grad." + k]) < 2e-4, k
+
+
+def test_sia_net_golden():
+    dev = cuda()
+    g = load_golden("sia_net_small")
+    net = _net(g, dev, True)
+    pose, a = net(g["points"].to(dev), g["lrfs"].to(dev), g["act"].to(dev), None)
+    assert pose.shape == g["pose"].shape
+    assert quat_err(pose.cpu(), g["pose"]) < TOL
+    assert max_err(a.cpu(), g["agreement"]) < TOL
+    tgt = torch.stack([g["labels"], g["labels"]], 1).to(dev)
+    loss = net.spread_loss(a, tgt, 0) + net.pose_diff_loss(pose)
+    assert abs(float(loss) - float(g["loss"])) < 1e-5
+    loss.backward()
+    for k, v in net.named_parameters():
+        assert rel_err(v.grad.cpu(), g["grad." + k]) < 2e-4, k
+
+
+def test_net_vs_oracle_seeded():
+    """same seeded synthetic ModelNet40-shaped inputs through the CUDA net and the
+    float64 oracle (B=2, C=32, 10 classes)."""
+    import qecnetworks_b200 as qb
+
+    dev = cuda()
+    params = orc.init_net_params(32, 10, seed=4)
+    points, lrfs, act, labels = orc.synthetic_batch(2, seed=21)
+    p64 = {k: v.double().requires_grad_(True) for k, v in params.items()}
+    pose_ref, a_ref = orc.qec_net_forward(p64, points.double(), lrfs.double(), act.double(), 3)
+    orc.spread_loss(a_ref, labels).backward()
+    net = qb.QecNet(2048, 32, 10, 3)
+    net.load_state_dict(params)
+    net = net.to(dev)
+    pose, a = net(points.to(dev), lrfs.to(dev), act.to(dev), None)
+    assert quat_err(pose.cpu(), pose_ref) < TOL
+    assert max_err(a.cpu(), a_ref) < TOL
+    net.spread_loss(a, labels.to(dev)).backward()
+    for k, v in net.named_parameters():
+        assert rel_err(v.grad.cpu(), p64[k].grad) < 2e-4, k
+
+
+def test_full_size_properties():
+    """BASELINE config 2 shapes (B=32, C=128, 40 classes, T=3): size-independent
+    properties -- unit-norm poses in the w>=0 hemisphere, activations in (0,1),
+    rotation equivariance (poses become q (x) pose up to sign, activations
+    unchanged), finite gradients for every parameter."""
+    import qecnetworks_b200 as qb
+
+    dev = cuda()
+    torch.manual_seed(0)
+    net = qb.QecNet(2048, 128, 40, 3).to(dev)
+    points, lrfs, act, labels = orc.synthetic_batch(32, seed=5)
+    points, lrfs, act, labels = points.to(dev), lrfs.to(dev), act.to(dev), labels.to(dev)
+    pose, a = net(points, lrfs, act, None)
+    assert pose.shape == (32, 40, 4) and a.shape == (32, 40)
+    assert float((pose.norm(dim=-1) - 1).abs().max()) < 1e-5
+    assert float(pose[..., 0].min()) >= 0.0
+    assert float(a.min()) > 0.0 and float(a.max()) < 1.0
+    net.spread_loss(a, labels).backward()
+    for k, v in net.named_parameters():
+        assert torch.isfinite(v.grad).all(), k
+        assert float(v.grad.abs().max()) > 0.0, k
+    q = torch.tensor([0.3, -0.5, 0.7, 0.4], device=dev)
+    q = q / q.norm()
+    qe = q.expand(32, 256, 9, 4)
+
+    def ham(a_, b_):
+        return orc.ham(a_, b_)
+
+    points_r = orc.qrotv(qe, points)
+    lrfs_r = ham(qe, lrfs)
+    lrfs_r = lrfs_r * torch.where(lrfs_r[..., :1] < 0, -1.0, 1.0)
+    with torch.no_grad():
+        pose_r, a_r = net(points_r, lrfs_r, act, None)
+    assert max_err(a_r.cpu(), a.detach().cpu()) < TOL
+    assert quat_err(ham(q.expand_as(pose), pose.detach()).cpu(), pose_r.cpu()) < 5e-4
