@@ -1,0 +1,413 @@
+#!/usr/bin/env python3
+"""bench.py -- QEC-Net training throughput on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU arm (oracle port)
+
+A "step" is one full training step of QEC-Net classification on one synthetic
+ModelNet40-shaped batch (BASELINE.json configs[1]: B=32 per GPU, 256 patches x 9-NN,
+128 channels, 40 classes, 3 routing iterations): forward, spread loss, backward, the
+data-parallel gradient all-reduce (N > 1) and the Adam update.  Weak scaling: the
+per-GPU batch is fixed, `value` is the whole-job samples/s (max over ranks of the
+CUDA-event time).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "QEC-Net samples/sec fwd+bwd"
+UNIT = "samples/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="samples per GPU (weak scaling)")
+    ap.add_argument("--channels", type=int, default=128)
+    ap.add_argument("--classes", type=int, default=40)
+    ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return ("configs[1]: full QEC-Net classification train step (fwd + spread loss + bwd + Adam), B=%d per GPU, "
+            "256 patches x 9-NN, C=%d, %d classes, T=%d, synthetic clustered LRFs" % (a.batch, a.channels, a.classes, a.iters))
+
+
+# ------------------------------------------------------------------ CPU arm (oracle port)
+def cpu_train_step_factory(a, batch):
+    """The reference's CPU path restated (oracle/qec_oracle.py, eigh in place of cuSOLVER),
+    noise ON as shipped, all host threads."""
+    import torch
+    from oracle import qec_oracle as orc
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    params = {k: v.requires_grad_(True) for k, v in orc.init_net_params(a.channels, a.classes, seed=0).items()}
+    opt = torch.optim.Adam(list(params.values()), lr=1e-3)
+    points, lrfs, act, labels = orc.synthetic_batch(batch, ncls=a.classes, seed=1234)
+
+    def step():
+        opt.zero_grad()
+        _, agr = orc.qec_net_forward(params, points, lrfs, act, a.iters, noise=1e-6)
+        loss = orc.spread_loss(agr, labels)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    return step
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_b = 2
+    step = cpu_train_step_factory(a, sample_b)
+    for _ in range(a.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(a.steps, 1)
+    value = sample_b / dt
+    cores = os.cpu_count() or 1
+    sample = "oracle port of the reference CPU path (torch eigh), B=%d per step, same net/config, noise on" % sample_b
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "per_step_sample": sample_b},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, p in zip(names, parts[3:7]):
+                if p == "Active":
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------ roofline accounting
+def kernel_work(name, dims, T):
+    """Algorithmic bytes / FLOP per launch.
+    Nv votes, Nc output capsules, Nn input LRFs."""
+    if name in ("qec_routing_fwd", "qec_routing_bwd"):
+        BP, O, J, T = dims[:4]
+        Nv, Nc, Nn = BP * O * J, BP * O, BP * J
+        if name == "qec_routing_fwd":
+            return 16 * Nv + 4 * Nn + 20 * Nc, 49 * T * Nv + 2000 * T * Nc + 20 * Nc
+        return 32 * Nv + 4 * Nn + 20 * Nc, 2 * 49 * T * Nv + 300 * T * Nc
+    if name in ("qec_votes_fwd", "qec_votes_bwd"):
+        BP, K, I, O = dims[:4]
+        Nv, Nn = BP * K * I * O, BP * K * I
+        if name == "qec_votes_fwd":
+            return 32 * Nv + 16 * Nn, 48 * Nv
+        return 48 * Nv + 32 * Nn, 2 * 48 * Nv
+    if name in ("qec_lrf_mean_fwd", "qec_lrf_mean_bwd"):
+        BP, K, I = dims[:3]
+        Nn, Nm = BP * K * I, BP * I
+        return (16 + 4 + 12 + 12) * Nn + 16 * Nm, 40 * Nn + 2000 * Nm
+    return 0, 0
+
+
+def measure_fp32_peak(torch, _lib, dev):
+    out = torch.zeros(1 << 20, device=dev)
+    blocks, iters = 148 * 16, 4096
+    flop = 2.0 * 16 * iters * 256 * blocks
+    best = 0.0
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.call("qec_ffma_peak", out.data_ptr(), blocks, iters, st)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, flop / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except (KeyError, ValueError):
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------ the B200 arm
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+
+    import qecnetworks_b200 as qb
+    from qecnetworks_b200 import _lib, ddp
+    from qecnetworks_b200.synthetic import synthetic_batch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: the QEC kernels have no CPU fallback")
+    rank, world, local = ddp.init_from_env("nccl")
+    if world != a.gpus and world > 1:
+        a.gpus = world
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(0)
+    net = qb.QecNet(2048, a.channels, a.classes, a.iters).to(dev)
+    ddp.broadcast_parameters(net, 0)
+    bucket = ddp.FlatGradBucket(net.parameters())
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=True)  # train_cls.py:44-51
+
+    NB = 4  # distinct batches rotated through the timed region
+    host = [synthetic_batch(a.batch, ncls=a.classes, seed=1234 + 1000 * rank + i, pin=True) for i in range(NB)]
+    devb = [tuple(t.to(dev) for t in hb) for hb in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+
+    def train_step(points, lrfs, act, labels):
+        bucket.zero()
+        _, agr = net(points, lrfs, act, None)
+        loss = net.spread_loss(agr, labels)
+        loss.backward()
+        bucket.all_reduce_mean()
+        opt.step()
+        return loss
+
+    # optional CUDA graph of the whole step (static input buffers)
+    static = tuple(torch.empty_like(t) for t in devb[0])
+    graph = None
+    static_loss = None
+
+    def load_static(b):
+        for s, t in zip(static, b):
+            s.copy_(t, non_blocking=True)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(max(a.warmup, 3)):  # W >= 3 untimed warm-up steps (also settles Adam state / allocator)
+            load_static(devb[i % NB])
+            train_step(*static)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    if not a.no_graph and world == 1:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = train_step(*static)
+        except Exception as e:  # capture is an optimisation, not a requirement
+            if rank == 0:
+                sys.stderr.write("CUDA graph capture failed (%s); running eagerly\n" % (e,))
+            graph = None
+            torch.cuda.synchronize()
+
+    def run_step(b, from_host=False):
+        for s, t in zip(static, b):
+            s.copy_(t, non_blocking=True)  # H2D from pinned memory when from_host
+        if graph is not None:
+            graph.replay()
+            return static_loss
+        return train_step(*static)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # launches inside a replayed graph do not pass through the ctypes counter: count one eager step
+    l0 = qb.kernel_launches()
+    train_step(*static)
+    launches_per_step = qb.kernel_launches() - l0
+    torch.cuda.synchronize()
+
+    # ---- timed region 1: inputs resident in HBM ---------------------------------------
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        run_step(devb[i % NB])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / a.steps
+
+    # ---- timed region 2: end to end from pinned host buffers, loss read back every step --
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    last = 0.0
+    for i in range(a.steps):
+        last = float(run_step(host[i % NB], from_host=True).item())  # D2H of the loss: one sync per step
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1) / a.steps
+    clocks = sampler.stop()
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    # ---- per-kernel pass (eager, CUDA events around every library call) ------------------
+    kernels = []
+    roofline = None
+    fp32_peak = None
+    if rank == 0:
+        fp32_peak = measure_fp32_peak(torch, _lib, dev)
+        hbm_peak, peak_src = load_peaks()
+        _lib.start_kernel_timing()
+        nprof = 3
+        for i in range(nprof):
+            for s, tt in zip(static, devb[i % NB]):
+                s.copy_(tt)
+            train_step(*static)
+        torch.cuda.synchronize()
+        rec = _lib.stop_kernel_timing()
+        tot = 0.0
+        for (name, dims), times in rec.items():
+            per = sum(times) / len(times)
+            calls = len(times) / nprof
+            by, fl = kernel_work(name, dims, a.iters)
+            kernels.append({
+                "kernel": name, "dims": list(dims), "calls_per_step": calls, "ms": per, "ms_per_step": per * calls,
+                "alg_bytes": by, "alg_flop": fl,
+                "hbm_gbs": by / (per * 1e-3) / 1e9 if per > 0 else None,
+                "hbm_frac": by / (per * 1e-3) / 1e9 / hbm_peak if per > 0 else None,
+                "fp32_tflops": fl / (per * 1e-3) / 1e12 if per > 0 else None,
+                "fp32_frac": fl / (per * 1e-3) / 1e12 / fp32_peak if per > 0 and fp32_peak else None,
+            })
+            tot += per * calls
+        kernels.sort(key=lambda k: -k["ms_per_step"])
+        for k in kernels:
+            k["share_of_step"] = k["ms_per_step"] / ms if ms > 0 else None
+        if kernels:
+            top = kernels[0]
+            hbm_time = top["alg_bytes"] / (hbm_peak * 1e9)
+            fp_time = top["alg_flop"] / (fp32_peak * 1e12)
+            if hbm_time >= fp_time:
+                roofline = {"kernel": top["kernel"], "dims": top["dims"], "bound": "hbm", "achieved": top["hbm_gbs"],
+                            "peak": hbm_peak, "unit": "GB/s", "frac": top["hbm_frac"], "traffic": None,
+                            "peak_source": peak_src, "ms": top["ms"]}
+            else:
+                roofline = {"kernel": top["kernel"], "dims": top["dims"], "bound": "fp32", "achieved": top["fp32_tflops"],
+                            "peak": fp32_peak, "unit": "TFLOP/s", "frac": top["fp32_frac"], "traffic": None,
+                            "peak_source": "FFMA microbenchmark in this run (qec_ffma_peak)", "ms": top["ms"],
+                            "note": "FP32-FMA-bound by design (4x4 quaternion algebra is not a dense contraction); "
+                                    "schema extension of hbm|tensor"}
+            roofline["own_kernels_ms_per_step"] = tot
+
+    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ----------------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        sample_b = 4
+        cstep = cpu_train_step_factory(a, sample_b)
+        cstep()
+        best = float("inf")
+        for _ in range(2):
+            t0 = time.perf_counter()
+            cstep()
+            best = min(best, time.perf_counter() - t0)
+        cpu = {"value": sample_b / best, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "oracle port of the reference CPU path (torch eigh in place of cuSOLVER, 1e-6 noise on), "
+                         "one train step at B=%d, best of 2 after 1 warm-up" % sample_b}
+
+    if rank == 0:
+        gb = a.batch * world
+        out = {
+            "metric": METRIC, "value": gb / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "global_batch": gb, "per_gpu_batch": a.batch,
+                       "parallelism": "dp%d" % world, "cuda_graph": graph is not None,
+                       "l2": "no explicit flush: the step streams >2 GB of vote/transform tensors per GPU "
+                             "(pool2 alone 671 MB x several passes), far above the 126 MB L2; %d distinct input "
+                             "batches are rotated" % NB,
+                       "grad_allreduce_bytes": bucket.nbytes() if world > 1 else 0},
+            "clocks": clocks,
+            "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches_per_step * a.steps,
+            "gpu_launches_per_step": launches_per_step,
+            "roofline": roofline,
+            "fp32_peak_tflops": fp32_peak,
+            "cpu_baseline": cpu,
+            "kernels": kernels,
+            "final_loss": last,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

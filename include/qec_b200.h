@@ -99,6 +99,11 @@ int qec_gather(const float* point_set, const float* lrf_set, const long long* id
                const int* wrong_count, float* points, float* lrfs, float* act, int* err, int B, int N, int P, int K,
                int Wmax, void* stream);
 
+/* FP32 FMA roof: blocks*256 threads x iters x 16 dependent-chain FMAs
+ * (2*16*iters*256*blocks FLOP); timed by the caller with CUDA events.  No reference
+ * counterpart: it measures the denominator of the FP32 roofline on the box. */
+int qec_ffma_peak(float* out, int blocks, int iters, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,11 +25,13 @@ SIGNATURES = {
     "qec_symeig4_fwd": ([_P, _P, _P, _P, _LL, _P], 1),
     "qec_symeig4_bwd": ([_P, _P, _P, _P, _P, _LL, _I, _P], 1),
     "qec_gather": ([_P] * 9 + [_I, _I, _I, _I, _I, _P], 1),
+    "qec_ffma_peak": ([_P, _I, _I, _P], 1),
 }
 
 _lib = None
 _lock = threading.Lock()
 _launches = 0
+_timing = None  # list of (name, int-args, start event, end event) while kernel timing is on
 
 
 class QecLibraryError(RuntimeError):
@@ -61,7 +63,17 @@ def call(name, *args):
     """Invoke an entry point; raise on a non-zero status."""
     global _launches
     fn = getattr(load(), name)
-    rc = fn(*args)
+    if _timing is not None:
+        import torch
+
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()  # on torch's current stream == the stream the kernels are launched on
+        rc = fn(*args)
+        e1.record()
+        _timing.append((name, tuple(a for a in args[:-1] if isinstance(a, int) and a < (1 << 31)), e0, e1))
+    else:
+        rc = fn(*args)
     if rc != 0:
         if rc < 0:
             raise QecLibraryError("%s: argument %d is invalid" % (name, -rc))
@@ -72,6 +84,22 @@ def call(name, *args):
 def launches():
     """Number of kernels of this library launched by this process so far."""
     return _launches
+
+
+def start_kernel_timing():
+    """record CUDA events around every entry-point call (bench.py's per-kernel roofline pass)"""
+    global _timing
+    _timing = []
+
+
+def stop_kernel_timing():
+    """-> {(name, dims): [ms, ...]}; the caller must have synchronised the device"""
+    global _timing
+    rec, _timing = _timing, None
+    out = {}
+    for name, dims, e0, e1 in rec or []:
+        out.setdefault((name, dims), []).append(e0.elapsed_time(e1))
+    return out
 
 
 def ptr(t):

@@ -179,7 +179,8 @@ __device__ __forceinline__ void routing_backward_capsule(const Coop& coop, const
                     const float direct = top ? gsn * om[t] : gb * a * om[t];
                     if (t > L) {
                         const float uv = qdot(uh[t], v);
-                        gb = fmaf(uv * x[t], rS[t], direct);
+                        // w = b * [a != 0]: the mask carries no gradient but gates the M-path
+                        gb = (a != 0.f) ? fmaf(uv * x[t], rS[t], direct) : direct;
                         if (top && write_gv) {
                             const float gx = gd * dist_grad(x[t]);
                             const float wh = b[t] * rS[t];

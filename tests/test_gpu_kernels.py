@@ -163,28 +163,42 @@ def _routing_case(B, P, O, J, T, frac, seed, need_act=True):
     Gp = torch.randn(B, P, O, 4, generator=gen)
     Ga = torch.randn(B, P, O, generator=gen)
 
-    v64 = votes.double().requires_grad_(True)
-    a64 = act.double().requires_grad_(need_act)
-    al64 = alpha.double().requires_grad_(True)
-    be64 = beta.double().requires_grad_(True)
-    pose_ref, agr_ref, poses_ref = orc.routing(v64, a64, al64, be64, T, return_all=True)
-    ((pose_ref * Gp.double()).sum() + (agr_ref * Ga.double()).sum()).backward()
+    def run_oracle(dt):
+        v = votes.to(dt).requires_grad_(True)
+        a = act.to(dt).requires_grad_(need_act)
+        al = alpha.to(dt).requires_grad_(True)
+        be = beta.to(dt).requires_grad_(True)
+        pose_o, agr_o = orc.routing(v, a, al, be, T)
+        ((pose_o * Gp.to(dt)).sum() + (agr_o * Ga.to(dt)).sum()).backward()
+        return pose_o.detach(), agr_o.detach(), v.grad, (a.grad if need_act else None), al.grad, be.grad
+
+    ref = run_oracle(torch.float64)
+    r32 = run_oracle(torch.float32)  # the reference's own arithmetic: its distance to float64 is the noise floor
 
     vd = votes.to(dev).requires_grad_(True)
     ad = act.to(dev).requires_grad_(need_act)
     ald = alpha.to(dev).requires_grad_(True)
     bed = beta.to(dev).requires_grad_(True)
     pose, agr = QF.routing(vd, ad, ald, bed, T)
-    assert quat_err(pose.cpu(), pose_ref) < TOL
-    assert max_err(agr.cpu(), agr_ref) < TOL
+    assert quat_err(pose.cpu(), ref[0]) < TOL
+    assert max_err(agr.cpu(), ref[1]) < TOL
     if B * P > 1:
         assert float(pose[-1, -1, 0].abs().max()) == 0.0
     ((pose * Gp.to(dev)).sum() + (agr * Ga.to(dev)).sum()).backward()
-    assert rel_err(vd.grad.cpu(), v64.grad) < TOL
+
+    def close(got, k):
+        # 1e-4, or 3x the float32 reference's own deviation from float64 where that is
+        # larger: D'(x) = -(2/pi)/sqrt(1-x^2) next to the 0.9999 clamp turns one float32
+        # ulp of <pose,vote> into a 3e-4 relative change of that vote's gradient.
+        tol = max(TOL, 3.0 * rel_err(r32[k], ref[k]))
+        e = rel_err(got.cpu(), ref[k])
+        assert e < tol, (k, e, tol)
+
+    close(vd.grad, 2)
     if need_act:
-        assert rel_err(ad.grad.cpu(), a64.grad) < TOL
-    assert rel_err(ald.grad.cpu(), al64.grad) < TOL
-    assert rel_err(bed.grad.cpu(), be64.grad) < TOL
+        close(ad.grad, 3)
+    close(ald.grad, 4)
+    close(bed.grad, 5)
 
 
 @pytest.mark.parametrize(

@@ -1,0 +1,151 @@
+"""CPU: host-side logic -- the C-ABI library loads and exports every symbol that
+include/qec_b200.h declares, the drop-in modules keep the reference's constructor /
+state_dict contract, the product refuses CPU tensors instead of falling back, and the
+data-parallel gradient bucket works across 2 gloo ranks."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "qec_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return re.findall(r"\bint\s+(qec_\w+)\s*\(", src)
+
+
+def test_library_exports_every_declared_symbol():
+    from qecnetworks_b200 import build, _lib
+
+    build.build()  # nvcc cross-compiles for sm_100a without a GPU
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), n
+        assert n in _lib.SIGNATURES, n
+    assert set(_lib.SIGNATURES) == set(names)
+    assert lib.qec_b200_version() == 100
+
+
+def test_argument_validation_without_gpu():
+    """negative return = index of the offending argument; no kernel is launched"""
+    from qecnetworks_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.qec_routing_fwd(None, None, None, None, None, None, None, None, 1, 1, 1, 3, None) == -1
+    assert lib.qec_votes_fwd(None, None, None, 1, 1, 1, 1, None) == -1
+    assert lib.qec_symeig4_fwd(None, None, None, None, 4, None) == -1
+    with pytest.raises(_lib.QecLibraryError):
+        _lib.call("qec_votes_fwd", None, None, None, 1, 1, 1, 1, None)
+
+
+def test_module_contract_matches_reference():
+    import qecnetworks_b200 as qb
+
+    m = qb.QecModule(in_channels=4, out_channels=6, num_iterations=3, num_neighbours=5, num_patches=3)
+    sd = m.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {
+        "alpha": (1,), "beta": (1,),
+        "quater_gen1.weight": (6, 12), "quater_gen1.bias": (6,),
+        "quater_gen2.weight": (96, 6), "quater_gen2.bias": (96,),
+    }
+    assert float(sd["alpha"]) == 1.0 and float(sd["beta"]) == 1.0
+    net = qb.QecNet(2048, 16, 10, 3)
+    keys = set(net.state_dict())
+    assert keys == {p + k for p in ("pool1.", "pool2.") for k in sd}
+    assert net.pool1.num_neighbours == 9 and net.pool1.num_patches == 256
+    assert net.pool2.num_neighbours == 256 and net.pool2.num_patches == 1
+    assert set(qb.QecSiaNet(2048, 16, 10, 3).state_dict()) == keys
+
+
+def test_no_cpu_fallback():
+    import qecnetworks_b200 as qb
+    from qecnetworks_b200._lib import QecLibraryError
+
+    m = qb.QecModule(1, 4, 3, 9, 8)
+    with pytest.raises(QecLibraryError):
+        m(torch.zeros(2, 8, 9, 3), torch.zeros(2, 8, 9, 1, 4), torch.zeros(2, 8, 9, 1))
+    with pytest.raises(QecLibraryError):
+        qb.symeig(torch.zeros(3, 4, 4))
+    with pytest.raises(NotImplementedError):
+        qb.symeig(torch.zeros(3, 5, 5))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "qecnetworks_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_losses_match_oracle():
+    from oracle import qec_oracle as orc
+    import qecnetworks_b200 as qb
+
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(6, 10, generator=g)
+    t = torch.randint(0, 10, (6,), generator=g)
+    net = qb.QecNet(2048, 4, 10, 3)
+    assert abs(float(net.spread_loss(x, t.view(-1, 1), 0)) - float(orc.spread_loss(x, t))) < 1e-7
+    pose = torch.randn(2, 6, 10, 4, generator=g)
+    pose = pose / pose.norm(dim=-1, keepdim=True)
+    assert abs(float(net.pose_diff_loss(pose)) - float(orc.pose_diff_loss(pose))) < 1e-7
+
+
+def test_synthetic_batch_shapes():
+    from qecnetworks_b200.synthetic import synthetic_batch, siamese_pair
+
+    points, lrfs, act, labels = synthetic_batch(3, ncls=40, seed=7)
+    assert points.shape == (3, 256, 9, 3) and lrfs.shape == (3, 256, 9, 4) and act.shape == (3, 256, 9)
+    n = lrfs.norm(dim=-1)
+    assert torch.all((n - act).abs() < 1e-5)  # unit where active, zero where not
+    assert float(lrfs[..., 0].min()) >= 0.0
+    assert torch.all(act[:, :, 0] == 1)
+    p2, l2, a2 = siamese_pair(points, lrfs, act)
+    assert p2.shape == (3, 2, 256, 9, 3) and l2.shape == (3, 2, 256, 9, 4) and a2.shape == (3, 2, 256, 9)
+    assert torch.all((l2[:, 1].norm(dim=-1) - act).abs() < 1e-5)
+
+
+def _ddp_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from qecnetworks_b200 import ddp
+    import qecnetworks_b200 as qb
+
+    r, w, _ = ddp.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    torch.manual_seed(100 + rank)  # different init per rank: broadcast must fix it
+    net = qb.QecNet(2048, 4, 5, 3)
+    ddp.broadcast_parameters(net, 0)
+    bucket = ddp.FlatGradBucket(net.parameters())
+    assert bucket.nbytes() == 4 * sum(p.numel() for p in net.parameters())
+    bucket.zero()
+    for i, p in enumerate(net.parameters()):
+        p.grad.add_(float(rank + 1) * (i + 1))  # grads are views into the flat buffer
+    bucket.all_reduce_mean()
+    expect = sum(range(1, world + 1)) / world
+    ok = all(torch.allclose(p.grad, torch.full_like(p, expect * (i + 1))) for i, p in enumerate(net.parameters()))
+    first = next(net.parameters()).detach().clone()
+    gathered = [torch.zeros_like(first) for _ in range(world)]
+    dist.all_gather(gathered, first)
+    same = all(torch.equal(gathered[0], t) for t in gathered)
+    lo, hi = ddp.shard_batch(32, rank, world)
+    out[rank] = bool(ok and same and (hi - lo) == 32 // world)
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_gloo_world2():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29611 + os.getpid() % 200
+    mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] and out[1]

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import qec_oracle as orc
-from tests.util import load_golden, params_of, quat_err, max_err, rel_err
+from tests.util import load_golden, params_of, quat_err, max_err, rel_err, grads_close
 
 TOL = 1e-4  # BASELINE.json north_star tolerance (fp32, quaternions up to sign)
 
@@ -102,8 +102,8 @@ def test_net_golden():
     loss = orc.spread_loss(a, g["labels"])
     assert abs(float(loss) - float(g["loss"])) < 1e-5
     loss.backward()
-    for k, v in params.items():
-        assert rel_err(v.grad, g["grad." + k]) < 2e-4, k
+    got = {k: v.grad for k, v in params.items()}
+    assert grads_close(got, {k: g["grad." + k] for k in got}, TOL) == []
 
 
 def test_sia_net_golden():
@@ -117,8 +117,8 @@ def test_sia_net_golden():
     loss = orc.sia_spread_loss(a, g["labels"]) + orc.pose_diff_loss(pose)
     assert abs(float(loss) - float(g["loss"])) < 1e-5
     loss.backward()
-    for k, v in params.items():
-        assert rel_err(v.grad, g["grad." + k]) < 2e-4, k
+    got = {k: v.grad for k, v in params.items()}
+    assert grads_close(got, {k: g["grad." + k] for k in got}, TOL) == []
 
 
 def test_equivariance():
