@@ -17,6 +17,15 @@ from torch.nn import Linear, Module, Parameter
 from . import functional as QF
 
 
+def _linear_bias_in_gemm(x, weight, bias):
+    """y = [x, 1] @ [W, b]^T.  Same value as F.linear(x, W, b), but the bias rides inside the
+    SGEMM (K+1) instead of a separate epilogue pass over the 671 MB output, and its gradient
+    falls out of the weight-gradient GEMM instead of a separate 671 MB reduction."""
+    xa = torch.cat([x, x.new_ones(x.shape[0], 1)], dim=1)
+    wa = torch.cat([weight, bias.unsqueeze(1)], dim=1)
+    return xa @ wa.t()
+
+
 class QecModule(Module):
     def __init__(self, in_channels, out_channels, num_iterations=3, num_neighbours=8, num_patches=8):
         super().__init__()
@@ -51,7 +60,8 @@ class QecModule(Module):
         lrfs = lrfs.float().contiguous()
         activation = activation.float().contiguous()
         _, xrot = QF.lrf_mean_rotate(lrfs, activation, points)
-        t_raw = self.quater_gen2(self.quater_gen1(xrot.view(B * P * K, 3 * I)))
+        h = self.quater_gen1(xrot.view(B * P * K, 3 * I))
+        t_raw = _linear_bias_in_gemm(h, self.quater_gen2.weight, self.quater_gen2.bias)
         votes = QF.votes(lrfs, t_raw)
         pose, agreement = QF.routing(votes, activation.view(B, P, K * I), self.alpha, self.beta, self.num_iterations)
         return pose.squeeze(-2), agreement
