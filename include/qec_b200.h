@@ -77,6 +77,24 @@ int qec_routing_bwd(const float* votes, const float* act, const float* alpha, co
                     const float* poses_all, const float* stats, const float* g_pose, const float* g_agreement,
                     float* g_votes, float* g_act, float* g_alpha_beta, int BP, int O, int J, int T, void* stream);
 
+/* Fused, cluster-resident variant of qec_votes_* + qec_routing_* for capsules with thousands
+ * of votes (J = K*I up to 32768; the pool2 layer).  Same reference functions as above
+ * (models/qec_module.py:126-147 and 172-194) but the [BP,O,J,4] vote tensor is never
+ * materialised: votes are generated into shared memory across a thread-block cluster.
+ *   t_oqi [BP*K, 4*I*O]: the output of quater_gen2 with its weight rows permuted to the
+ *   capsule-major feature order o*4I + q*I + i (instead of q*I*O + i*O + o).
+ * qec_routing_fused_supported returns 1/0 (not a status).  Backward: g_toqi [BP*K,4*I*O]
+ * overwritten; g_lrfs [BP,K,I,4] and g_act [BP,J] nullable and ACCUMULATED (caller zero-fills);
+ * g_alpha_beta [2] ACCUMULATED. */
+int qec_routing_fused_supported(int K, int I, int O, int T);
+int qec_routing_fused_fwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
+                          const float* beta, float* pose, float* agreement, float* poses_all, float* stats, int BP,
+                          int K, int I, int O, int T, void* stream);
+int qec_routing_fused_bwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
+                          const float* beta, const float* poses_all, const float* stats, const float* g_pose,
+                          const float* g_agreement, float* g_toqi, float* g_lrfs, float* g_act, float* g_alpha_beta,
+                          int BP, int K, int I, int O, int T, void* stream);
+
 /* torch_autograd_solver.symeig on [n,4,4] (torch_autograd_solver/__init__.py:141-159,
  * 74-81 -> torch_cusolver.cpp:194-288): w [n,4] ascending, V [n,4,4] with ROWS =
  * eigenvectors, upper triangle of the row-major input.

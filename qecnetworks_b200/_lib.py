@@ -22,6 +22,9 @@ SIGNATURES = {
     "qec_votes_bwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _P], 1),
     "qec_routing_fwd": ([_P] * 8 + [_I, _I, _I, _I, _P], 1),
     "qec_routing_bwd": ([_P] * 11 + [_I, _I, _I, _I, _P], 1),
+    "qec_routing_fused_supported": ([_I, _I, _I, _I], 0),
+    "qec_routing_fused_fwd": ([_P] * 9 + [_I, _I, _I, _I, _I, _P], 1),
+    "qec_routing_fused_bwd": ([_P] * 13 + [_I, _I, _I, _I, _I, _P], 1),
     "qec_symeig4_fwd": ([_P, _P, _P, _P, _LL, _P], 1),
     "qec_symeig4_bwd": ([_P, _P, _P, _P, _P, _LL, _I, _P], 1),
     "qec_gather": ([_P] * 9 + [_I, _I, _I, _I, _I, _P], 1),
@@ -79,6 +82,11 @@ def call(name, *args):
             raise QecLibraryError("%s: argument %d is invalid" % (name, -rc))
         raise QecLibraryError("%s: CUDA error %d at launch" % (name, rc))
     _launches += SIGNATURES[name][1]
+
+
+def query(name, *args):
+    """entry points that return a value rather than a status"""
+    return getattr(load(), name)(*args)
 
 
 def launches():

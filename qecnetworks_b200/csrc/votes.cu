@@ -10,7 +10,7 @@
 // the raw transform components through shared memory with rows read coalesced
 // along `o`, then computes with lanes running along `j` so that every vote is
 // one float4 store into a contiguous run of the capsule's row.
-#include "qec_common.cuh"
+#include "vote_math.cuh"
 
 namespace qec {
 
@@ -35,29 +35,6 @@ __device__ __forceinline__ void stage_traw(float* sm, const float* __restrict__ 
     }
 }
 
-struct VoteParts {
-    Quat that;   // normalised transform (before the hemisphere fix)
-    float rn;    // 1 / max(|t_raw|, 1e-12)
-    float st;    // sign(that.w)
-    float sv;    // sign((lrf (x) t).w)
-    Quat t;      // fix(that)
-    Quat vote;
-};
-
-__device__ __forceinline__ VoteParts make_vote(Quat lrf, Quat traw) {
-    VoteParts r;
-    const float n2 = qdot(traw, traw);
-    // F.normalize: x / max(|x|, eps)
-    r.rn = (n2 > 1e-24f) ? frsqrt(n2) : 1e12f;
-    r.that = qscale(traw, r.rn);
-    r.st = fsign(r.that.w);
-    r.t = qscale(r.that, r.st);
-    const Quat h = qham(lrf, r.t);
-    r.sv = fsign(h.w);
-    r.vote = qscale(h, r.sv);
-    return r;
-}
-
 __global__ void __launch_bounds__(kVT)
     votes_fwd_kernel(const float* __restrict__ lrfs, const float* __restrict__ t_raw, float* __restrict__ votes,
                      int K, int I, int O, int ntj, int nto) {
@@ -79,16 +56,6 @@ __global__ void __launch_bounds__(kVT)
         const VoteParts vp = make_vote(lrf, traw);
         stq_stream(votes + (((size_t)bp * O + o0 + ol) * J + j0 + jl) * 4, vp.vote);
     }
-}
-
-// adjoint of make_vote: g = dL/dvote -> dL/dt_raw, dL/dlrf
-__device__ __forceinline__ void vote_bwd(Quat lrf, const VoteParts& vp, Quat g, Quat& g_traw, Quat& g_lrf) {
-    const Quat gh = qscale(g, vp.sv);
-    g_lrf = qham(gh, qconj(vp.t));                  // d(l (x) t)/dl
-    const Quat gt = qscale(qham(qconj(lrf), gh), vp.st);  // d/d that
-    // normalisation Jacobian (I - that that^T) / |t_raw|   (identity / eps if clamped)
-    const float proj = (vp.rn < 1e12f) ? qdot(vp.that, gt) : 0.f;
-    g_traw = qscale(qfma(-proj, vp.that, gt), vp.rn);
 }
 
 __global__ void __launch_bounds__(kVT)

@@ -17,12 +17,14 @@ from torch.nn import Linear, Module, Parameter
 from . import functional as QF
 
 
-def _linear_bias_in_gemm(x, weight, bias):
+def _linear_bias_in_gemm(x, weight, bias, row_perm=None):
     """y = [x, 1] @ [W, b]^T.  Same value as F.linear(x, W, b), but the bias rides inside the
     SGEMM (K+1) instead of a separate epilogue pass over the 671 MB output, and its gradient
     falls out of the weight-gradient GEMM instead of a separate 671 MB reduction."""
     xa = torch.cat([x, x.new_ones(x.shape[0], 1)], dim=1)
     wa = torch.cat([weight, bias.unsqueeze(1)], dim=1)
+    if row_perm is not None:
+        wa = wa.index_select(0, row_perm)  # output features re-ordered for free inside the GEMM
     return xa @ wa.t()
 
 
@@ -61,7 +63,28 @@ class QecModule(Module):
         activation = activation.float().contiguous()
         _, xrot = QF.lrf_mean_rotate(lrfs, activation, points)
         h = self.quater_gen1(xrot.view(B * P * K, 3 * I))
-        t_raw = _linear_bias_in_gemm(h, self.quater_gen2.weight, self.quater_gen2.bias)
-        votes = QF.votes(lrfs, t_raw)
-        pose, agreement = QF.routing(votes, activation.view(B, P, K * I), self.alpha, self.beta, self.num_iterations)
+        act_flat = activation.view(B, P, K * I)
+        if K * I >= self.FUSED_MIN_VOTES and QF.routing_fused_supported(K, I, O, self.num_iterations):
+            # capsule-major transforms straight out of the GEMM; votes never touch HBM
+            t_oqi = _linear_bias_in_gemm(h, self.quater_gen2.weight, self.quater_gen2.bias, self._oqi_perm(I, O))
+            pose, agreement = QF.routing_fused(t_oqi, lrfs, act_flat, self.alpha, self.beta, self.num_iterations)
+        else:
+            t_raw = _linear_bias_in_gemm(h, self.quater_gen2.weight, self.quater_gen2.bias)
+            votes = QF.votes(lrfs, t_raw)
+            pose, agreement = QF.routing(votes, act_flat, self.alpha, self.beta, self.num_iterations)
         return pose.squeeze(-2), agreement
+
+    FUSED_MIN_VOTES = 1024  # below this a whole CTA per capsule is wasteful: general path
+
+    def _oqi_perm(self, I, O):
+        """row permutation of quater_gen2 that turns the reference feature order q*I*O + i*O + o
+        (qec_module.py:126) into the capsule-major order o*4I + q*I + i"""
+        dev = self.quater_gen2.weight.device
+        perm = getattr(self, "_perm_cache", None)
+        if perm is None or perm.device != dev or perm.numel() != 4 * I * O:
+            o = torch.arange(O, device=dev).view(O, 1, 1)
+            q = torch.arange(4, device=dev).view(1, 4, 1)
+            i = torch.arange(I, device=dev).view(1, 1, I)
+            perm = (q * (I * O) + i * O + o).reshape(-1)
+            self._perm_cache = perm
+        return perm

@@ -256,3 +256,85 @@ def test_gather_bit_exact():
     bad[0, 0, 0] = N + 3
     _, _, _, err = QF.neighbour_gather(ps.to(dev), ls.to(dev), bad.to(dev))
     assert int(err.item()) == 1
+
+
+# ---------------------------------------------------------------- fused cluster-resident routing
+def _oqi_perm(I, O):
+    o = torch.arange(O).view(O, 1, 1)
+    q = torch.arange(4).view(1, 4, 1)
+    i = torch.arange(I).view(1, 1, I)
+    return (q * (I * O) + i * O + o).reshape(-1)
+
+
+@pytest.mark.parametrize(
+    "B,P,K,I,O,T",
+    [
+        (2, 1, 64, 32, 5, 3),     # J = 2048, one CTA per capsule
+        (1, 2, 100, 37, 3, 3),    # J = 3700, ragged channels
+        (1, 1, 256, 24, 4, 3),    # J = 6144, cluster of 2
+        (1, 1, 250, 50, 3, 2),    # J = 12500, cluster of 4, ragged split, T = 2
+        (1, 1, 256, 128, 6, 3),   # J = 32768, cluster of 8 (pool2 of BASELINE config 2)
+        (1, 1, 256, 128, 2, 1),   # T = 1
+    ],
+)
+def test_routing_fused(B, P, K, I, O, T):
+    from qecnetworks_b200 import functional as QF
+
+    dev = cuda()
+    assert QF.routing_fused_supported(K, I, O, T)
+    gen = torch.Generator().manual_seed(K * 7 + I)
+    J = K * I
+    lrfs = clustered((B, P, K, I), gen, spread=0.3)
+    act = (torch.rand(B, P, J, generator=gen) * 0.6 + 0.3) * (torch.rand(B, P, J, generator=gen) < 0.85)
+    act[:, :, 0] = 1.0
+    lrfs = lrfs * (act.view(B, P, K, I, 1) != 0)  # inactive neighbours carry a zero LRF
+    base = torch.randn(1, 4, 1, O, generator=gen)
+    t_raw = (base + 0.25 * torch.randn(B * P * K, 4, I, O, generator=gen)).reshape(B * P * K, 4 * I * O)
+    perm = _oqi_perm(I, O)
+    alpha, beta = torch.tensor([1.2]), torch.tensor([0.8])
+    Gp = torch.randn(B, P, O, 4, generator=gen)
+    Ga = torch.randn(B, P, O, generator=gen)
+
+    def run_oracle(dt):
+        l = lrfs.clone().to(dt).requires_grad_(True)
+        t = t_raw.clone().to(dt).requires_grad_(True)
+        a = act.clone().to(dt).requires_grad_(True)
+        al = alpha.clone().to(dt).requires_grad_(True)
+        be = beta.clone().to(dt).requires_grad_(True)
+        v = orc.votes_from(l, t.view(B, P, K, 4, I, O))
+        pose_o, agr_o = orc.routing(v, a, al, be, T)
+        ((pose_o * Gp.to(dt)).sum() + (agr_o * Ga.to(dt)).sum()).backward()
+        return pose_o.detach(), agr_o.detach(), t.grad, l.grad, a.grad, al.grad, be.grad
+
+    ref = run_oracle(torch.float64)
+    r32 = run_oracle(torch.float32)
+
+    ld = lrfs.to(dev).requires_grad_(True)
+    td = t_raw[:, perm].contiguous().to(dev).requires_grad_(True)
+    ad = act.to(dev).requires_grad_(True)
+    ald = alpha.to(dev).requires_grad_(True)
+    bed = beta.to(dev).requires_grad_(True)
+    pose, agr = QF.routing_fused(td, ld, ad, ald, bed, T)
+    assert quat_err(pose.cpu(), ref[0]) < TOL
+    assert max_err(agr.cpu(), ref[1]) < TOL
+    ((pose * Gp.to(dev)).sum() + (agr * Ga.to(dev)).sum()).backward()
+    g_traw = torch.empty_like(t_raw)
+    g_traw[:, perm] = td.grad.cpu()
+
+    def close(got, k):
+        tol = max(TOL, 3.0 * rel_err(r32[k], ref[k]))
+        e = rel_err(got, ref[k])
+        assert e < tol, (k, e, tol)
+
+    close(g_traw, 2)
+    close(ld.grad.cpu(), 3)
+    close(ad.grad.cpu(), 4)
+    close(ald.grad.cpu(), 5)
+    close(bed.grad.cpu(), 6)
+
+    # and the fused path agrees with the general path (materialised votes) on the same input
+    l2 = lrfs.to(dev).requires_grad_(True)
+    t2 = t_raw.to(dev).requires_grad_(True)
+    pose2, agr2 = QF.routing(QF.votes(l2, t2), act.to(dev), alpha.to(dev), beta.to(dev), T)
+    assert quat_err(pose.detach().cpu(), pose2.detach().cpu()) < 1e-5
+    assert max_err(agr.detach().cpu(), agr2.detach().cpu()) < 1e-5
