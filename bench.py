@@ -164,6 +164,20 @@ def kernel_work(name, dims, T):
         if name == "qec_votes_fwd":
             return 32 * Nv + 16 * Nn, 48 * Nv
         return 48 * Nv + 32 * Nn, 2 * 48 * Nv
+    if name in ("qec_routing_fused_fwd", "qec_routing_fused_bwd"):
+        # votes generated on chip from the transforms: t read once (fwd) + its gradient written once (bwd)
+        BP, K, I, O, T = dims[:5]
+        Nv, Nc, Nn = BP * K * I * O, BP * O, BP * K * I
+        if name == "qec_routing_fused_fwd":
+            return 16 * Nv + 20 * Nn + 20 * Nc, (48 + 49 * T) * Nv + 2000 * T * Nc + 20 * Nc
+        return 32 * Nv + 40 * Nn + 20 * Nc, (2 * 48 + 2 * 49 * T) * Nv + 300 * T * Nc
+    if name in ("qec_routing_small_fwd", "qec_routing_small_bwd"):
+        # I = 1, composed transform (24 FLOP / vote) evaluated in-kernel: no transform tensor at all
+        BP, K, O, T = dims[:4]
+        Nv, Nc, Nn = BP * K * O, BP * O, BP * K
+        if name == "qec_routing_small_fwd":
+            return 32 * Nn + 20 * Nc, (24 + 48 + 49 * T) * Nv + 2000 * T * Nc + 20 * Nc
+        return 32 * Nn + (16 * T + 28) * Nc, (2 * (24 + 48) + 49 * (T + 1)) * Nv + 300 * Nc
     if name in ("qec_lrf_mean_fwd", "qec_lrf_mean_bwd"):
         BP, K, I = dims[:3]
         Nn, Nm = BP * K * I, BP * I

@@ -95,6 +95,22 @@ int qec_routing_fused_bwd(const float* t_oqi, const float* lrfs, const float* ac
                           const float* g_agreement, float* g_toqi, float* g_lrfs, float* g_act, float* g_alpha_beta,
                           int BP, int K, int I, int O, int T, void* stream);
 
+/* Register-resident variant for in_channels = 1 and K <= 16 neighbours (the pool1 layer): the
+ * two Linears of get_votes have no non-linearity between them (models/qec_module.py:123-124), so
+ * t_raw = Wc x + bc with Wc = W2 W1 [4*O,3], bc = W2 b1 + b2 [4*O] (row q*O + o) composed by the
+ * caller; the kernel covers qec_module.py:123-147 and 172-194 without the [BP*K, 4*O] tensor.
+ *   xrot [BP,K,3] (from qec_lrf_mean_fwd), lrfs [BP,K,4], act [BP,K]
+ * Backward: only parameter gradients (g_Wc [4*O,3], g_bc [4*O], g_alpha_beta [2], all ACCUMULATED);
+ * callers that need dL/dlrfs, dL/dact or dL/dpoints use qec_votes_* + qec_routing_*. */
+int qec_routing_small_supported(int K, int I, int O, int T);
+int qec_routing_small_fwd(const float* xrot, const float* lrfs, const float* act, const float* Wc, const float* bc,
+                          const float* alpha, const float* beta, float* pose, float* agreement, float* poses_all,
+                          float* stats, int BP, int K, int O, int T, void* stream);
+int qec_routing_small_bwd(const float* xrot, const float* lrfs, const float* act, const float* Wc, const float* bc,
+                          const float* alpha, const float* beta, const float* poses_all, const float* stats,
+                          const float* g_pose, const float* g_agreement, float* g_Wc, float* g_bc,
+                          float* g_alpha_beta, int BP, int K, int O, int T, void* stream);
+
 /* torch_autograd_solver.symeig on [n,4,4] (torch_autograd_solver/__init__.py:141-159,
  * 74-81 -> torch_cusolver.cpp:194-288): w [n,4] ascending, V [n,4,4] with ROWS =
  * eigenvectors, upper triangle of the row-major input.

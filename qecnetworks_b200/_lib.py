@@ -25,6 +25,9 @@ SIGNATURES = {
     "qec_routing_fused_supported": ([_I, _I, _I, _I], 0),
     "qec_routing_fused_fwd": ([_P] * 9 + [_I, _I, _I, _I, _I, _P], 1),
     "qec_routing_fused_bwd": ([_P] * 13 + [_I, _I, _I, _I, _I, _P], 1),
+    "qec_routing_small_supported": ([_I, _I, _I, _I], 0),
+    "qec_routing_small_fwd": ([_P] * 11 + [_I, _I, _I, _I, _P], 1),
+    "qec_routing_small_bwd": ([_P] * 14 + [_I, _I, _I, _I, _P], 1),
     "qec_symeig4_fwd": ([_P, _P, _P, _P, _LL, _P], 1),
     "qec_symeig4_bwd": ([_P, _P, _P, _P, _P, _LL, _I, _P], 1),
     "qec_gather": ([_P] * 9 + [_I, _I, _I, _I, _I, _P], 1),

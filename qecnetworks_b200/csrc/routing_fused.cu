@@ -14,14 +14,17 @@
 // lrfs[bp,k,i,:] is one coalesced float4 load and the activation one coalesced float load.
 //
 // Residency.  A thread-block cluster of CL CTAs (CL = 1, 2, 4, 8) owns one capsule at a
-// time; CTA r holds votes [r*Jc, (r+1)*Jc) as float4 in its shared memory (Jc <= 4096:
-// 64 KB, two CTAs per SM so that one capsule's eigen-solve latency hides behind another's
-// sweeps).  Each sweep reduces 10-15 floats inside the CTA (warp shuffles + shared memory),
-// publishes the CTA partial in its own shared memory, cluster-barriers, and every CTA sums
-// all partials through distributed shared memory in the same fixed order, so all CTAs of
-// the cluster run the same Jacobi / Cholesky solve on identical inputs and no pose
-// broadcast across CTAs is needed.  HBM traffic per capsule: the transforms once (forward),
-// plus their gradient once (backward).
+// time; CTA r holds votes [r*Jc, (r+1)*Jc), Jc <= 4096, as float4 in its shared memory
+// together with the per-vote routing state, so every sweep after the first touches no
+// global memory at all:
+//   forward : vote + (activation, routing weight b)             24 B / vote,  2 CTAs / SM
+//   backward: vote + <pose^t,v>, 1-d^t for all t + g_b + g_a    48 B / vote,  1 CTA  / SM
+// Each sweep reduces <= 16 floats: a value-splitting warp butterfly (16 SHFL instead of 80),
+// one shared-memory stage across the warps, then the CTA partial is published in shared
+// memory, the cluster barriers, and every CTA sums all partials through distributed shared
+// memory in the same fixed order -- all CTAs of the cluster then run the same Jacobi /
+// Cholesky solve on identical inputs, so no pose broadcast across CTAs is needed.
+// HBM traffic per capsule: the transforms once (forward), plus their gradient once (backward).
 #include <cooperative_groups.h>
 
 #include "routing_core.cuh"
@@ -32,70 +35,77 @@ namespace cg = cooperative_groups;
 namespace qec {
 
 constexpr int kFT = 512;      // threads per CTA
+constexpr int kFW = kFT / 32;
 constexpr int kJcMax = 4096;  // resident votes per CTA
-constexpr int kCoopN = 16;
+constexpr int kTB = 3;        // routing iterations the cached backward supports
+
+// After this, lane L holds (in the return value) the warp-wide total of a[idx16(L)].
+__device__ __forceinline__ int idx16(int lane) { return (lane >> 1) & 15; }
+__device__ __forceinline__ float warp_reduce_scatter16(float (&a)[16], int lane) {
+#pragma unroll
+    for (int h = 8, bit = 16; h >= 1; h >>= 1, bit >>= 1) {
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < h) {
+                const float send = up ? a[i] : a[i + h];
+                const float keep = up ? a[i + h] : a[i];
+                a[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+            }
+        }
+    }
+    return a[0] + __shfl_xor_sync(0xffffffffu, a[0], 1);
+}
 
 template <int CL>
-struct ClusterCoop {
-    static constexpr int kWarps = kFT / 32;
-    float* scratch;  // [kCoopN * kWarps] intra-CTA staging
-    float* part;     // [2][kCoopN] this CTA's published partial sums (double-buffered)
-    float* out;      // [kCoopN] solve result broadcast inside the CTA
-    mutable unsigned phase;
-    __device__ __forceinline__ ClusterCoop(float* s) : scratch(s), part(s + kCoopN * kWarps),
-                                                       out(s + kCoopN * kWarps + 2 * kCoopN), phase(0) {}
-    static constexpr int kSmemFloats = kCoopN * kWarps + 3 * kCoopN;
-    __device__ __forceinline__ int first() const { return threadIdx.x; }
-    __device__ __forceinline__ int stride() const { return kFT; }
-    // totals end up valid in every lane of warp 0 of EVERY CTA of the cluster
+struct ClusterReducer {
+    float* scratch;  // [16][kFW] warp partials
+    float* part;     // [2][16] this CTA's published partial sums (double-buffered across sweeps)
+    float* out;      // [16] solve result broadcast inside the CTA
+    unsigned phase;
+    __device__ __forceinline__ explicit ClusterReducer(float* s)
+        : scratch(s), part(s + 16 * kFW), out(s + 16 * kFW + 32), phase(0) {}
+    static constexpr int kSmemFloats = 16 * kFW + 48;
+
+    // Sum a[0..N) over every thread of every CTA of the cluster.  On return the totals are
+    // valid in all lanes of warp 0 of every CTA (identical bits in every CTA).
     template <int N>
-    __device__ __forceinline__ void reduce(float (&a)[N]) const {
-        static_assert(N <= kCoopN, "accumulator too wide");
+    __device__ __forceinline__ void reduce(float (&a)[N]) {
+        static_assert(N <= 16, "accumulator too wide");
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        float w[16];
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], s);
-        }
-        __syncthreads();
-        if (lane == 0) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) scratch[i * kWarps + warp] = a[i];
-        }
+        for (int i = 0; i < 16; ++i) w[i] = (i < N) ? a[i] : 0.f;
+        const float mine_v = warp_reduce_scatter16(w, lane);
+        __syncthreads();  // scratch / out may still be read from the previous round
+        if ((lane & 1) == 0) scratch[idx16(lane) * kFW + warp] = mine_v;
         __syncthreads();
         if (warp == 0) {
+            float s = 0.f;
+            if (lane < 16) {
 #pragma unroll
-            for (int i = 0; i < N; ++i) {
-                float s = 0.f;
-#pragma unroll
-                for (int w = 0; w < kWarps; ++w) s += scratch[i * kWarps + w];
-                a[i] = s;
+                for (int x = 0; x < kFW; ++x) s += scratch[lane * kFW + x];  // fixed order
             }
-        }
-        if (CL > 1) {
-            cg::cluster_group cluster = cg::this_cluster();
-            float* mine = part + (phase & 1u) * kCoopN;
-            if (threadIdx.x == 0) {
+            if (CL > 1) {
+                float* mine = part + (phase & 1u) * 16;
+                if (lane < 16) mine[lane] = s;
+                cg::this_cluster().sync();  // all threads of all CTAs (see below)
+                s = 0.f;
+                if (lane < 16) {
 #pragma unroll
-                for (int i = 0; i < N; ++i) mine[i] = a[i];
-            }
-            cluster.sync();  // release/acquire: every CTA's partial is visible cluster-wide
-            if (warp == 0) {
-                float s = 0.f;
-                if (lane < N) {
-#pragma unroll
-                    for (int r = 0; r < CL; ++r) s += cluster.map_shared_rank(mine, r)[lane];  // DSMEM, fixed order
+                    for (int r = 0; r < CL; ++r) s += cg::this_cluster().map_shared_rank(mine, r)[lane];
                 }
-#pragma unroll
-                for (int i = 0; i < N; ++i) a[i] = __shfl_sync(0xffffffffu, s, i);
             }
-            ++phase;
+#pragma unroll
+            for (int i = 0; i < N; ++i) a[i] = __shfl_sync(0xffffffffu, s, i);
+        } else if (CL > 1) {
+            cg::this_cluster().sync();
         }
+        ++phase;
     }
     __device__ __forceinline__ bool solver() const { return threadIdx.x < 32; }
     template <int N>
-    __device__ __forceinline__ void bcast(float (&r)[N]) const {
-        static_assert(N <= kCoopN, "result too wide");
+    __device__ __forceinline__ void bcast(float (&r)[N]) {
         if (threadIdx.x == 0) {
 #pragma unroll
             for (int i = 0; i < N; ++i) out[i] = r[i];
@@ -103,15 +113,6 @@ struct ClusterCoop {
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < N; ++i) r[i] = out[i];
-    }
-    __device__ __forceinline__ bool leader() const { return threadIdx.x == 0; }
-};
-
-struct VotesShared {
-    const float4* sv;
-    __device__ __forceinline__ Quat get(int jl) const {
-        const float4 v = sv[jl];
-        return qmake(v.x, v.y, v.z, v.w);
     }
 };
 
@@ -124,34 +125,24 @@ __device__ __forceinline__ void red_add_q(float* p, Quat q) {  // REDG.E.ADD.F32
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(q.w), "f"(q.x), "f"(q.y), "f"(q.z)
                  : "memory");
 }
+__device__ __forceinline__ Quat lds_q(const float4* p) {
+    const float4 v = *p;
+    return qmake(v.x, v.y, v.z, v.w);
+}
+__device__ __forceinline__ void sts_q(float4* p, Quat q) { *p = make_float4(q.w, q.x, q.y, q.z); }
 
-struct CapsuleGeom {
-    const float* t_oqi;  // [BP*K, 4*I*O]
-    const float* lrfs;   // [BP*K*I, 4]
-    long long bp;
-    int o, K, I, O, j_begin;
-    __device__ __forceinline__ void locate(int j, size_t& toff, size_t& loff) const {
-        const int k = j / I, i = j - k * I;
-        const size_t row = (size_t)bp * K + k;
-        toff = row * (size_t)(4 * I * O) + (size_t)o * 4 * I + i;
-        loff = row * I + i;
+// walks this thread's votes jl = tid, tid + kFT, ... of the CTA's slice, tracking (k, i) of
+// j = j_begin + jl = k*I + i without a division per vote
+struct VoteWalker {
+    int k, i, dk, di, I;
+    __device__ __forceinline__ VoteWalker(int j_begin, int I_) : I(I_) {
+        const int j = j_begin + threadIdx.x;
+        k = j / I;
+        i = j - k * I;
+        dk = kFT / I;
+        di = kFT - dk * I;
     }
-};
-
-// generate this CTA's votes into shared memory (each thread later re-reads only its own slots)
-__device__ __forceinline__ void generate_votes(const CapsuleGeom& g, float4* sv, int nloc) {
-    const int I = g.I;
-    int j = g.j_begin + threadIdx.x;
-    int k = j / I, i = j - k * I;
-    const int dk = kFT / I, di = kFT - dk * I;
-    for (int jl = threadIdx.x; jl < nloc; jl += kFT) {
-        const size_t row = (size_t)g.bp * g.K + k;
-        const float* tp = g.t_oqi + row * (size_t)(4 * I * g.O) + (size_t)g.o * 4 * I + i;
-        const Quat traw = qmake(ldg_stream_f32(tp), ldg_stream_f32(tp + I), ldg_stream_f32(tp + 2 * I),
-                                ldg_stream_f32(tp + 3 * I));
-        const Quat lrf = ldq_nc(g.lrfs + (row * I + i) * 4);
-        const Quat v = make_vote(lrf, traw).vote;
-        sv[jl] = make_float4(v.w, v.x, v.y, v.z);
+    __device__ __forceinline__ void next() {
         i += di;
         k += dk;
         if (i >= I) {
@@ -159,34 +150,20 @@ __device__ __forceinline__ void generate_votes(const CapsuleGeom& g, float4* sv,
             ++k;
         }
     }
-}
-
-// receives dL/dvote for local vote jl: recompute the vote's parts from the (L2-resident)
-// transform and LRF, push the gradient through fix / Hamilton / fix / normalise
-struct SinkFused {
-    CapsuleGeom g;
-    float* g_toqi;
-    float* g_lrfs;  // nullable
-    __device__ __forceinline__ void put(int jl, Quat gv) {
-        size_t toff, loff;
-        g.locate(g.j_begin + jl, toff, loff);
-        const int I = g.I;
-        const float* tp = g.t_oqi + toff;
-        const Quat traw = qmake(__ldg(tp), __ldg(tp + I), __ldg(tp + 2 * I), __ldg(tp + 3 * I));
-        const Quat lrf = ldq_nc(g.lrfs + loff * 4);
-        const VoteParts vp = make_vote(lrf, traw);
-        Quat gt, gl;
-        vote_bwd(lrf, vp, gv, gt, gl);
-        float* gp = g_toqi + toff;
-        gp[0] = gt.w;
-        gp[I] = gt.x;
-        gp[2 * I] = gt.y;
-        gp[3 * I] = gt.z;
-        if (g_lrfs != nullptr) red_add_q(g_lrfs + loff * 4, gl);  // sum over the O capsules of the patch
-    }
 };
 
-template <int CL, int TMAX>
+__device__ __forceinline__ Quat solve_pose(const float* acc, bool valid) {
+    const Sym4 m = acc_to_sym(acc, 1.f / fmaxf(acc[10], 1e-12f));  // F.normalize(p=1) of the weights
+    float lam;
+    Quat p = qfix(top_eigvec(m, lam, WarpDone()));
+    if (!valid) p = qmake(0.f, 0.f, 0.f, 0.f);
+    return p;
+}
+
+// ------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------
+template <int CL>
 __global__ void __launch_bounds__(kFT, 2)
     routing_fused_fwd_kernel(const float* __restrict__ t_oqi, const float* __restrict__ lrfs,
                              const float* __restrict__ act, const float* __restrict__ alpha_p,
@@ -195,7 +172,8 @@ __global__ void __launch_bounds__(kFT, 2)
                              float* __restrict__ stats, long long Nc, int K, int I, int O, int T) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* sv = reinterpret_cast<float4*>(smem_raw);
-    ClusterCoop<CL> coop(reinterpret_cast<float*>(sv + kJcMax));
+    float2* sab = reinterpret_cast<float2*>(sv + kJcMax);  // (activation, routing weight b)
+    ClusterReducer<CL> red(reinterpret_cast<float*>(sab + kJcMax));
     int rank = 0;
     if (CL > 1) rank = (int)cg::this_cluster().block_rank();
     const long long cid = blockIdx.x / CL, ncl = gridDim.x / CL;
@@ -204,34 +182,184 @@ __global__ void __launch_bounds__(kFT, 2)
     const int j_begin = min(J, rank * Jc);
     const int nloc = min(J, j_begin + Jc) - j_begin;
     const float alpha = __ldg(alpha_p), beta = __ldg(beta_p);
+    const size_t trow = (size_t)4 * I * O;
+    const bool writer = (rank == 0) && (threadIdx.x == 0);
+
     for (long long c = cid; c < Nc; c += ncl) {
         const long long bp = c / O;
-        CapsuleGeom g{t_oqi, lrfs, bp, (int)(c - bp * O), K, I, O, j_begin};
-        generate_votes(g, sv, nloc);
-        VotesShared vs{sv};
-        const float* act_row = act + (size_t)bp * J + j_begin;
-        Quat ph[TMAX];
-#pragma unroll
-        for (int t = 0; t < TMAX; ++t) ph[t] = qmake(0.f, 0.f, 0.f, 0.f);
-        float s, n;
-        const float agr = routing_forward_capsule<TMAX>(coop, vs, act_row, nloc, T, alpha, beta, ph, s, n);
-        if (rank == 0 && coop.leader()) {
-#pragma unroll
-            for (int t = 0; t < TMAX; ++t)
-                if (t < T) {
-                    stq(poses_all + ((size_t)t * Nc + c) * 4, ph[t]);
-                    if (t == T - 1) stq(pose + (size_t)c * 4, ph[t]);
-                }
-            agreement[c] = agr;
+        const int o = (int)(c - bp * O);
+        // ---- generate the votes (once) + sweep 0: M^0 = sum a v v^T, b^0 = a ----------------
+        float acc[12];
+        zero_acc(acc);
+        {
+            VoteWalker w(j_begin, I);
+            const float* tbase = t_oqi + (size_t)o * 4 * I;
+            for (int jl = threadIdx.x; jl < nloc; jl += kFT) {
+                const size_t row = (size_t)bp * K + w.k;
+                const float* tp = tbase + row * trow + w.i;
+                const Quat traw = qmake(ldg_stream_f32(tp), ldg_stream_f32(tp + I), ldg_stream_f32(tp + 2 * I),
+                                        ldg_stream_f32(tp + 3 * I));
+                const Quat lrf = ldq_nc(lrfs + (row * I + w.i) * 4);
+                const float a = __ldg(act + row * I + w.i);
+                const Quat v = make_vote(lrf, traw).vote;
+                sts_q(sv + jl, v);
+                sab[jl] = make_float2(a, a);
+                acc[10] += fabsf(a);
+                acc_rank1(acc, a, v);
+                acc[11] += (v.w + v.x) + (v.y + v.z);
+                w.next();
+            }
+        }
+        red.reduce(acc);
+        bool valid = false;
+        float r[4] = {0.f, 0.f, 0.f, 0.f};
+        if (red.solver()) {
+            valid = acc[11] != 0.f;  // reference qec_module.py:72-73
+            const Quat p = solve_pose(acc, valid);
+            r[0] = p.w; r[1] = p.x; r[2] = p.y; r[3] = p.z;
+        }
+        red.bcast(r);
+        Quat p = qmake(r[0], r[1], r[2], r[3]);
+        if (writer) stq(poses_all + (size_t)c * 4, p);
+        // ---- sweeps 1..T-1: b <- b a (1 - d(pose, v)), M^t = sum b v v^T, all from shared memory
+        for (int t = 1; t < T; ++t) {
+            float a2[11];
+            zero_acc(a2);
+#pragma unroll 2
+            for (int jl = threadIdx.x; jl < nloc; jl += kFT) {
+                const Quat v = lds_q(sv + jl);
+                const float2 ab = sab[jl];
+                const float b = ab.y * (ab.x * one_minus_dist(qdot(p, v)));
+                sab[jl].y = b;
+                a2[10] += fabsf(b);
+                acc_rank1(a2, b, v);
+            }
+            red.reduce(a2);
+            if (red.solver()) {
+                const Quat q = solve_pose(a2, valid);
+                r[0] = q.w; r[1] = q.x; r[2] = q.y; r[3] = q.z;
+            }
+            red.bcast(r);
+            p = qmake(r[0], r[1], r[2], r[3]);
+            if (writer) stq(poses_all + ((size_t)t * Nc + c) * 4, p);
+        }
+        // ---- epilogue sweep: inlier score (reference qec_module.py:188-193) ---------------------
+        float e[2] = {0.f, 0.f};
+#pragma unroll 2
+        for (int jl = threadIdx.x; jl < nloc; jl += kFT) {
+            const Quat v = lds_q(sv + jl);
+            const float b = sab[jl].y;
+            e[0] = fmaf(b, one_minus_dist(qdot(p, v)), e[0]);
+            e[1] += (b != 0.f) ? 1.f : 0.f;
+        }
+        red.reduce(e);
+        if (rank == 0 && threadIdx.x == 0) {
+            const float n = e[1];
+            const float s = (n > 0.f) ? e[0] / n : 0.f;
+            stq(pose + (size_t)c * 4, p);
+            agreement[c] = (n > 0.f) ? sigmoidf(fmaf(alpha, s, beta - 1.f)) : 0.f;
             stats[2 * c] = s;
             stats[2 * c + 1] = n;
         }
-        __syncthreads();  // the next capsule overwrites the resident votes
+        // the next capsule's reduce() starts with __syncthreads(): the resident votes are not
+        // overwritten while a warp is still sweeping (each thread only re-reads its own slots)
     }
     if (CL > 1) cg::this_cluster().sync();  // no CTA may exit while a peer can still read its partials
 }
 
-template <int CL, int TMAX>
+// ------------------------------------------------------------------------------------
+// backward (T <= kTB).  Levels t = T-1..0; sweep k completes level T-k (its adjoint vector u is
+// known from the previous reduction) and accumulates level T-k-1.  Per-vote quantities of the
+// forward chain (x^t = <pose^t, v>, 1 - d^t) are computed once in sweep 0 and cached in shared
+// memory; g_b of the last completed level and the running activation gradient are carried in
+// shared memory as well.  See routing_core.cuh for the algebra.
+// ------------------------------------------------------------------------------------
+struct BwdSmem {
+    float4* sv;
+    float* sx[kTB];
+    float* som[kTB];
+    float* sgb;
+    float* sga;
+};
+
+struct BwdSweepArgs {
+    BwdSmem sm;
+    int nloc, j_begin, I, K;
+    long long bp;
+    size_t trow;
+    const float* act;
+    const float* lrfs;
+    const float* tbase;
+    float* gtbase;
+    float* g_lrfs;     // nullable
+    float* g_act_row;  // nullable: no activation gradient -> only the top level is processed
+    Quat ut, pt;       // adjoint vector and pose of the level being completed
+    float rst, gsn;
+};
+
+// One backward sweep over this CTA's resident votes: completes level TT (TOP: TT = T-1, the
+// level whose votes are not detached -> writes dL/dt_raw, dL/dlrf) and accumulates level TT-1.
+template <int TT, bool TOP>
+__device__ __forceinline__ void bwd_sweep(const BwdSweepArgs& A, float (&acc)[15]) {
+    const bool chain = A.g_act_row != nullptr;
+    const bool more = chain && TT >= 1;
+    const bool last = chain && TT == 0;
+    const int I = A.I;
+    VoteWalker w(A.j_begin, I);
+    for (int jl = threadIdx.x; jl < A.nloc; jl += kFT) {
+        const Quat v = lds_q(A.sm.sv + jl);
+        const size_t row = (size_t)A.bp * A.K + w.k;
+        const float a = __ldg(A.act + row * I + w.i);
+        // b^TT and b^{TT-1} from the cached (1 - d) chain: b^{t+1} = b^t a (1 - d^t)
+        float b = a, blow = a;
+        if (TT >= 1) b = a * (a * A.sm.som[0][jl]);
+        if (TT >= 2) {
+            blow = b;
+            b = b * (a * A.sm.som[1][jl]);
+        }
+        const float x_t = A.sm.sx[TT][jl];
+        const float om_t = A.sm.som[TT][jl];
+        const float uv = qdot(A.ut, v);
+        float gb, ga;
+        if (TOP) {
+            gb = A.gsn * om_t;
+            ga = 0.f;
+            const float gx = -A.gsn * b * dist_grad(x_t);
+            const float wh = b * A.rst;
+            Quat gv = qscale(A.pt, fmaf(wh, uv, gx));  // p (gx + w <u,v>)
+            gv = qfma(wh * x_t, A.ut, gv);             // + u w <p,v>
+            const float* tp = A.tbase + row * A.trow + w.i;
+            const Quat traw = qmake(__ldg(tp), __ldg(tp + I), __ldg(tp + 2 * I), __ldg(tp + 3 * I));
+            const Quat lrf = ldq_nc(A.lrfs + (row * I + w.i) * 4);
+            const VoteParts vp = make_vote(lrf, traw);
+            Quat gt, gl;
+            vote_bwd(lrf, vp, gv, gt, gl);
+            float* gp = A.gtbase + row * A.trow + w.i;
+            gp[0] = gt.w; gp[I] = gt.x; gp[2 * I] = gt.y; gp[3 * I] = gt.z;
+            if (A.g_lrfs != nullptr) red_add_q(A.g_lrfs + (row * I + w.i) * 4, gl);  // sum over the O capsules
+        } else {
+            const float gprev = A.sm.sgb[jl];            // dL/db^{TT+1}
+            ga = fmaf(gprev * b, om_t, A.sm.sga[jl]);    // b^{TT+1} = b^TT a (1 - d^TT)
+            gb = gprev * a * om_t;
+        }
+        if (a != 0.f) gb = fmaf(uv * x_t, A.rst, gb);  // the M-path is gated by mask = [a != 0]
+        if (more) {
+            A.sm.sgb[jl] = gb;
+            A.sm.sga[jl] = ga;
+            // level TT-1: dL/dd_j = -g_b^TT b^{TT-1} a
+            const float x_l = A.sm.sx[TT >= 1 ? TT - 1 : 0][jl];
+            const float gx = -gb * blow * a * dist_grad(x_l);
+            acc[0] = fmaf(gx, v.w, acc[0]); acc[1] = fmaf(gx, v.x, acc[1]);
+            acc[2] = fmaf(gx, v.y, acc[2]); acc[3] = fmaf(gx, v.z, acc[3]);
+            acc_rank1(acc + 4, blow, v);
+            acc[14] += fabsf(blow);
+        }
+        if (last) atomicAdd(A.g_act_row + jl, ga + gb);  // + dL/db^0 (b^0 = a)
+        w.next();
+    }
+}
+
+template <int CL>
 __global__ void __launch_bounds__(kFT, 1)
     routing_fused_bwd_kernel(const float* __restrict__ t_oqi, const float* __restrict__ lrfs,
                              const float* __restrict__ act, const float* __restrict__ alpha_p,
@@ -240,8 +368,17 @@ __global__ void __launch_bounds__(kFT, 1)
                              const float* __restrict__ g_agr, float* __restrict__ g_toqi, float* g_lrfs, float* g_act,
                              float* g_alpha_beta, long long Nc, int K, int I, int O, int T) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* sv = reinterpret_cast<float4*>(smem_raw);
-    ClusterCoop<CL> coop(reinterpret_cast<float*>(sv + kJcMax));
+    BwdSmem sm;
+    sm.sv = reinterpret_cast<float4*>(smem_raw);
+    float* f = reinterpret_cast<float*>(sm.sv + kJcMax);
+#pragma unroll
+    for (int t = 0; t < kTB; ++t) {
+        sm.sx[t] = f + (2 * t) * kJcMax;
+        sm.som[t] = f + (2 * t + 1) * kJcMax;
+    }
+    sm.sgb = f + 2 * kTB * kJcMax;
+    sm.sga = sm.sgb + kJcMax;
+    ClusterReducer<CL> red(sm.sga + kJcMax);
     int rank = 0;
     if (CL > 1) rank = (int)cg::this_cluster().block_rank();
     const long long cid = blockIdx.x / CL, ncl = gridDim.x / CL;
@@ -250,43 +387,122 @@ __global__ void __launch_bounds__(kFT, 1)
     const int j_begin = min(J, rank * Jc);
     const int nloc = min(J, j_begin + Jc) - j_begin;
     const float alpha = __ldg(alpha_p), beta = __ldg(beta_p);
+    const size_t trow = (size_t)4 * I * O;
+    const bool need_chain = g_act != nullptr;
     float ga_tot = 0.f, gb_tot = 0.f;
+
     for (long long c = cid; c < Nc; c += ncl) {
         const long long bp = c / O;
-        CapsuleGeom g{t_oqi, lrfs, bp, (int)(c - bp * O), K, I, O, j_begin};
-        generate_votes(g, sv, nloc);
-        VotesShared vs{sv};
-        SinkFused sink{g, g_toqi, g_lrfs};
-        const float* act_row = act + (size_t)bp * J + j_begin;
-        float* g_act_row = (g_act != nullptr) ? g_act + (size_t)bp * J + j_begin : nullptr;
-        Quat ph[TMAX];
+        const int o = (int)(c - bp * O);
+        const float* tbase = t_oqi + (size_t)o * 4 * I;
+        float* gtbase = g_toqi + (size_t)o * 4 * I;
+        // per-capsule scalars
+        Quat ph[kTB], uh[kTB];
+        float rS[kTB];
 #pragma unroll
-        for (int t = 0; t < TMAX; ++t)
+        for (int t = 0; t < kTB; ++t) {
             ph[t] = (t < T) ? ldq_nc(poses_all + ((size_t)t * Nc + c) * 4) : qmake(0.f, 0.f, 0.f, 0.f);
-        float ga, gb;
-        routing_backward_capsule<TMAX>(coop, vs, sink, act_row, g_act_row, nloc, T, alpha, beta, ph,
-                                       __ldg(stats + 2 * c), __ldg(stats + 2 * c + 1),
-                                       ldq_nc(g_pose + (size_t)c * 4), __ldg(g_agr + c), g_act != nullptr, ga, gb);
-        ga_tot += ga;
-        gb_tot += gb;
-        __syncthreads();
+            uh[t] = qmake(0.f, 0.f, 0.f, 0.f);
+            rS[t] = 0.f;
+        }
+        const float s = __ldg(stats + 2 * c), n = __ldg(stats + 2 * c + 1);
+        const bool has = n > 0.f;
+        const float sg = sigmoidf(fmaf(alpha, s, beta - 1.f));
+        const float gz = has ? __ldg(g_agr + c) * sg * (1.f - sg) : 0.f;
+        ga_tot += gz * s;
+        gb_tot += gz;
+        const float gsn = has ? gz * alpha / n : 0.f;
+        const Quat gpose = ldq_nc(g_pose + (size_t)c * 4);
+
+        // ---- sweep 0: generate votes, forward chain (cached), accumulate level T-1 -----------
+        float acc[15];
+        zero_acc(acc);
+        {
+            VoteWalker w(j_begin, I);
+            for (int jl = threadIdx.x; jl < nloc; jl += kFT) {
+                const size_t row = (size_t)bp * K + w.k;
+                const float* tp = tbase + row * trow + w.i;
+                const Quat traw = qmake(ldg_stream_f32(tp), ldg_stream_f32(tp + I), ldg_stream_f32(tp + 2 * I),
+                                        ldg_stream_f32(tp + 3 * I));
+                const Quat lrf = ldq_nc(lrfs + (row * I + w.i) * 4);
+                const float a = __ldg(act + row * I + w.i);
+                const Quat v = make_vote(lrf, traw).vote;
+                sts_q(sm.sv + jl, v);
+                float b = a, xl = 0.f, bl = 0.f;
+#pragma unroll
+                for (int t = 0; t < kTB; ++t) {
+                    if (t < T) {
+                        const float x = qdot(ph[t], v);
+                        const float om = one_minus_dist(x);
+                        sm.sx[t][jl] = x;
+                        sm.som[t][jl] = om;
+                        xl = x;
+                        bl = b;  // b^t
+                        b *= a * om;
+                    }
+                }
+                // level T-1 (final distance): dL/dd_j = -gsn b^{T-1}_j
+                const float gx = -gsn * bl * dist_grad(xl);
+                acc[0] = fmaf(gx, v.w, acc[0]); acc[1] = fmaf(gx, v.x, acc[1]);
+                acc[2] = fmaf(gx, v.y, acc[2]); acc[3] = fmaf(gx, v.z, acc[3]);
+                acc_rank1(acc + 4, bl, v);
+                acc[14] += fabsf(bl);
+                w.next();
+            }
+        }
+        // ---- sweeps k = 1..: complete level t = T-k, accumulate level t-1 -------------------
+        const int nsweeps = need_chain ? T : 1;
+        for (int k = 1; k <= nsweeps; ++k) {
+            const int t = T - k;  // level being completed
+            // solve u^t from the reduction of the previous sweep
+            red.reduce(acc);
+            float r[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+            if (red.solver()) {
+                Quat p = ph[0];
+#pragma unroll
+                for (int u = 1; u < kTB; ++u)
+                    if (u == t) p = ph[u];
+                const float rs = 1.f / fmaxf(acc[14], 1e-12f);
+                const Sym4 m = acc_to_sym(acc + 4, rs);
+                Quat gp = qmake(acc[0], acc[1], acc[2], acc[3]);
+                if (t == T - 1) gp = qadd(gp, gpose);
+                const float lam = qdot(p, sym_mul(m, p));
+                Quat u = top_eigvec_adjoint(m, p, lam, gp);
+                if (!(qdot(p, p) > 0.5f)) u = qmake(0.f, 0.f, 0.f, 0.f);  // invalid / sign-zeroed pose
+                r[0] = u.w; r[1] = u.x; r[2] = u.y; r[3] = u.z; r[4] = rs;
+            }
+            red.bcast(r);
+            BwdSweepArgs a;
+            a.sm = sm; a.nloc = nloc; a.j_begin = j_begin; a.I = I; a.K = K; a.bp = bp; a.trow = trow;
+            a.act = act; a.lrfs = lrfs; a.tbase = tbase; a.gtbase = gtbase; a.g_lrfs = g_lrfs;
+            a.g_act_row = need_chain ? g_act + (size_t)bp * J + j_begin : nullptr;
+            a.ut = qmake(r[0], r[1], r[2], r[3]); a.rst = r[4]; a.gsn = gsn;
+            zero_acc(acc);
+            const bool top = (k == 1);
+            // the level index is a template parameter: the (1-d) chain, the cached loads and the
+            // top-level vote-gradient code fold at compile time
+            if (t == 2) { a.pt = ph[2]; bwd_sweep<2, true>(a, acc); }
+            else if (t == 1) { a.pt = ph[1]; if (top) bwd_sweep<1, true>(a, acc); else bwd_sweep<1, false>(a, acc); }
+            else { a.pt = ph[0]; if (top) bwd_sweep<0, true>(a, acc); else bwd_sweep<0, false>(a, acc); }
+        }
     }
-    if (rank == 0 && coop.leader()) {
+    if (rank == 0 && threadIdx.x == 0) {
         atomicAdd(g_alpha_beta, ga_tot);
         atomicAdd(g_alpha_beta + 1, gb_tot);
     }
     if (CL > 1) cg::this_cluster().sync();
 }
 
-constexpr size_t kFusedSmem = sizeof(float4) * kJcMax + sizeof(float) * (kCoopN * (kFT / 32) + 3 * kCoopN);
+constexpr size_t kRedBytes = sizeof(float) * (16 * kFW + 48);
+constexpr size_t kFwdSmem = (sizeof(float4) + sizeof(float2)) * kJcMax + kRedBytes;
+constexpr size_t kBwdSmem = (sizeof(float4) + sizeof(float) * (2 * kTB + 2)) * kJcMax + kRedBytes;
 
-// persistent grid: as many clusters as can be co-resident (the solve latency of one capsule
-// hides behind the sweeps of the others), never more than there are capsules
+// persistent grid: as many clusters as can be co-resident, never more than there are capsules
 template <class Kern>
-static int fused_grid(Kern kern, int CL, long long Nc, cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr,
-                      int& cached_clusters) {
+static int fused_grid(Kern kern, int CL, size_t smem, long long Nc, cudaLaunchConfig_t& cfg,
+                      cudaLaunchAttribute* attr, int& cached_clusters) {
     cfg.blockDim = dim3(kFT);
-    cfg.dynamicSmemBytes = kFusedSmem;
+    cfg.dynamicSmemBytes = smem;
     cfg.numAttrs = 0;
     cfg.attrs = attr;
     if (CL > 1) {
@@ -298,7 +514,7 @@ static int fused_grid(Kern kern, int CL, long long Nc, cudaLaunchConfig_t& cfg, 
     }
     int clusters = cached_clusters;  // per kernel instantiation; every B200 gives the same answer
     if (clusters < 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         if (CL > 1) {
             cfg.gridDim = dim3(CL * 2 * kNumSMs);  // upper bound for the occupancy query
@@ -306,7 +522,7 @@ static int fused_grid(Kern kern, int CL, long long Nc, cudaLaunchConfig_t& cfg, 
             if (e != cudaSuccess) return (int)e;
         } else {
             int per_sm = 0;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFT, kFusedSmem);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFT, smem);
             if (e != cudaSuccess) return (int)e;
             clusters = per_sm * kNumSMs;
         }
@@ -324,15 +540,15 @@ static int pick_cluster(int J) {
     return 0;
 }
 
-template <int CL, int TMAX>
+template <int CL>
 static int launch_fused_fwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
                             const float* beta, float* pose, float* agreement, float* poses_all, float* stats,
                             long long Nc, int K, int I, int O, int T, cudaStream_t st) {
-    auto kern = routing_fused_fwd_kernel<CL, TMAX>;
+    auto kern = routing_fused_fwd_kernel<CL>;
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     static int cached = -1;
-    const int rc = fused_grid(kern, CL, Nc, cfg, attr, cached);
+    const int rc = fused_grid(kern, CL, kFwdSmem, Nc, cfg, attr, cached);
     if (rc) return rc;
     cfg.stream = st;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, t_oqi, lrfs, act, alpha, beta, pose, agreement, poses_all,
@@ -340,16 +556,16 @@ static int launch_fused_fwd(const float* t_oqi, const float* lrfs, const float* 
     return e == cudaSuccess ? launch_status() : (int)e;
 }
 
-template <int CL, int TMAX>
+template <int CL>
 static int launch_fused_bwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
                             const float* beta, const float* poses_all, const float* stats, const float* g_pose,
                             const float* g_agr, float* g_toqi, float* g_lrfs, float* g_act, float* g_ab, long long Nc,
                             int K, int I, int O, int T, cudaStream_t st) {
-    auto kern = routing_fused_bwd_kernel<CL, TMAX>;
+    auto kern = routing_fused_bwd_kernel<CL>;
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     static int cached = -1;
-    const int rc = fused_grid(kern, CL, Nc, cfg, attr, cached);
+    const int rc = fused_grid(kern, CL, kBwdSmem, Nc, cfg, attr, cached);
     if (rc) return rc;
     cfg.stream = st;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, t_oqi, lrfs, act, alpha, beta, poses_all, stats, g_pose,
@@ -361,12 +577,12 @@ static int launch_fused_bwd(const float* t_oqi, const float* lrfs, const float* 
 
 using namespace qec;
 
-#define QEC_DISPATCH_CL(FN, ...)                          \
-    switch (CL) {                                         \
-        case 1: return FN<1, 3>(__VA_ARGS__);             \
-        case 2: return FN<2, 3>(__VA_ARGS__);             \
-        case 4: return FN<4, 3>(__VA_ARGS__);             \
-        default: return FN<8, 3>(__VA_ARGS__);            \
+#define QEC_DISPATCH_CL(FN, ...)               \
+    switch (CL) {                              \
+        case 1: return FN<1>(__VA_ARGS__);     \
+        case 2: return FN<2>(__VA_ARGS__);     \
+        case 4: return FN<4>(__VA_ARGS__);     \
+        default: return FN<8>(__VA_ARGS__);    \
     }
 
 // 1 if this geometry is served by the fused resident kernels, else 0 (callers then use
@@ -375,7 +591,7 @@ extern "C" int qec_routing_fused_supported(int K, int I, int O, int T) {
     if (K <= 0 || I <= 0 || O <= 0) return 0;
     const long long J = (long long)K * I;
     if (J > 8ll * kJcMax) return 0;
-    return (T >= 1 && T <= 3 && pick_cluster((int)J) > 0) ? 1 : 0;
+    return (T >= 1 && T <= kTB && pick_cluster((int)J) > 0) ? 1 : 0;
 }
 
 extern "C" int qec_routing_fused_fwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,

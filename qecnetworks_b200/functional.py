@@ -173,6 +173,62 @@ class RoutingFused(torch.autograd.Function):
         return g_toqi, g_lrfs, g_act, g_ab[0:1], g_ab[1:2], None
 
 
+class RoutingSmall(torch.autograd.Function):
+    """in_channels = 1: (xrot [B,P,K,1,3], lrfs [B,P,K,1,4], activation [B,P,K], Wc [4*O,3], bc [4*O],
+    alpha, beta, T) -> (pose [B,P,O,4], agreement [B,P,O]) with the composed transform Wc x + bc
+    evaluated in-kernel (qec_module.py:123-147 + 172-194).  Differentiable w.r.t. Wc, bc, alpha,
+    beta only; the caller falls back to votes() + routing() when the inputs need gradients."""
+
+    @staticmethod
+    def forward(ctx, xrot, lrfs, activation, Wc, bc, alpha, beta, num_iterations):
+        B, P, K = activation.shape
+        O = bc.shape[0] // 4
+        xrot = _check(xrot, "xrot", (B, P, K, 1, 3))
+        lrfs = _check(lrfs, "lrfs", (B, P, K, 1, 4))
+        activation = _check(activation, "activation", (B, P, K))
+        Wc = _check(Wc, "Wc", (4 * O, 3))
+        bc = _check(bc, "bc", (4 * O,))
+        alpha = _check(alpha, "alpha", (1,))
+        beta = _check(beta, "beta", (1,))
+        T = int(num_iterations)
+        dev = lrfs.device
+        pose = torch.empty(B, P, O, 4, device=dev, dtype=torch.float32)
+        agreement = torch.empty(B, P, O, device=dev, dtype=torch.float32)
+        poses_all = torch.empty(T, B, P, O, 4, device=dev, dtype=torch.float32)
+        stats = torch.empty(B, P, O, 2, device=dev, dtype=torch.float32)
+        call("qec_routing_small_fwd", ptr(xrot), ptr(lrfs), ptr(activation), ptr(Wc), ptr(bc), ptr(alpha), ptr(beta),
+             ptr(pose), ptr(agreement), ptr(poses_all), ptr(stats), B * P, K, O, T, _stream())
+        ctx.save_for_backward(xrot, lrfs, activation, Wc, bc, alpha, beta, poses_all, stats)
+        ctx.T = T
+        return pose, agreement
+
+    @staticmethod
+    def backward(ctx, g_pose, g_agreement):
+        xrot, lrfs, activation, Wc, bc, alpha, beta, poses_all, stats = ctx.saved_tensors
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            raise _lib.QecLibraryError("routing_small has no gradient w.r.t. its data inputs; use votes() + routing()")
+        B, P, K = activation.shape
+        O = bc.shape[0] // 4
+        dev = lrfs.device
+        g_pose = torch.zeros(B, P, O, 4, device=dev) if g_pose is None else g_pose.contiguous()
+        g_agreement = torch.zeros(B, P, O, device=dev) if g_agreement is None else g_agreement.contiguous()
+        g_Wc = torch.zeros_like(Wc)
+        g_bc = torch.zeros_like(bc)
+        g_ab = torch.zeros(2, device=dev, dtype=torch.float32)
+        call("qec_routing_small_bwd", ptr(xrot), ptr(lrfs), ptr(activation), ptr(Wc), ptr(bc), ptr(alpha), ptr(beta),
+             ptr(poses_all), ptr(stats), ptr(g_pose), ptr(g_agreement), ptr(g_Wc), ptr(g_bc), ptr(g_ab), B * P, K, O,
+             ctx.T, _stream())
+        return None, None, None, g_Wc, g_bc, g_ab[0:1], g_ab[1:2], None
+
+
+def routing_small_supported(K, I, O, T):
+    return bool(_lib.query("qec_routing_small_supported", int(K), int(I), int(O), int(T)))
+
+
+def routing_small(xrot, lrfs, activation, Wc, bc, alpha, beta, num_iterations):
+    return RoutingSmall.apply(xrot, lrfs, activation, Wc, bc, alpha, beta, num_iterations)
+
+
 def routing_fused_supported(K, I, O, T):
     return bool(_lib.query("qec_routing_fused_supported", int(K), int(I), int(O), int(T)))
 

@@ -62,8 +62,19 @@ class QecModule(Module):
         lrfs = lrfs.float().contiguous()
         activation = activation.float().contiguous()
         _, xrot = QF.lrf_mean_rotate(lrfs, activation, points)
-        h = self.quater_gen1(xrot.view(B * P * K, 3 * I))
         act_flat = activation.view(B, P, K * I)
+        data_grad = torch.is_grad_enabled() and (points.requires_grad or lrfs.requires_grad or activation.requires_grad)
+        if I == 1 and not data_grad and QF.routing_small_supported(K, I, O, self.num_iterations):
+            # no non-linearity between the two Linears: compose them (rank 3 for I = 1) and let the
+            # register-resident kernel evaluate Wc x + bc per vote -- no [B*P*K, 4*O] tensor, no GEMM
+            W1, b1 = self.quater_gen1.weight, self.quater_gen1.bias
+            W2, b2 = self.quater_gen2.weight, self.quater_gen2.bias
+            Wc = W2 @ W1
+            bc = torch.addmv(b2, W2, b1)
+            pose, agreement = QF.routing_small(xrot, lrfs, act_flat, Wc, bc, self.alpha, self.beta,
+                                               self.num_iterations)
+            return pose.squeeze(-2), agreement
+        h = self.quater_gen1(xrot.view(B * P * K, 3 * I))
         if K * I >= self.FUSED_MIN_VOTES and QF.routing_fused_supported(K, I, O, self.num_iterations):
             # capsule-major transforms straight out of the GEMM; votes never touch HBM
             t_oqi = _linear_bias_in_gemm(h, self.quater_gen2.weight, self.quater_gen2.bias, self._oqi_perm(I, O))

@@ -192,6 +192,7 @@ def _routing_case(B, P, O, J, T, frac, seed, need_act=True):
         # ulp of <pose,vote> into a 3e-4 relative change of that vote's gradient.
         tol = max(TOL, 3.0 * rel_err(r32[k], ref[k]))
         e = rel_err(got.cpu(), ref[k])
+        print("routing margin k=%d err=%.2e tol=%.2e" % (k, e, tol))
         assert e < tol, (k, e, tol)
 
     close(vd.grad, 2)
@@ -324,6 +325,7 @@ def test_routing_fused(B, P, K, I, O, T):
     def close(got, k):
         tol = max(TOL, 3.0 * rel_err(r32[k], ref[k]))
         e = rel_err(got, ref[k])
+        print("fused margin k=%d err=%.2e tol=%.2e" % (k, e, tol))
         assert e < tol, (k, e, tol)
 
     close(g_traw, 2)
@@ -338,3 +340,52 @@ def test_routing_fused(B, P, K, I, O, T):
     pose2, agr2 = QF.routing(QF.votes(l2, t2), act.to(dev), alpha.to(dev), beta.to(dev), T)
     assert quat_err(pose.detach().cpu(), pose2.detach().cpu()) < 1e-5
     assert max_err(agr.detach().cpu(), agr2.detach().cpu()) < 1e-5
+
+
+# ---------------------------------------------------------------- register-resident pool1 kernel
+@pytest.mark.parametrize("B,P,K,O,T", [(2, 8, 9, 16, 3), (1, 5, 9, 130, 3), (2, 3, 4, 7, 1), (1, 4, 13, 40, 2), (1, 2, 16, 33, 5)])
+def test_routing_small(B, P, K, O, T):
+    from qecnetworks_b200 import functional as QF
+
+    dev = cuda()
+    assert QF.routing_small_supported(K, 1, O, T)
+    gen = torch.Generator().manual_seed(K * 13 + O)
+    lrfs = clustered((B, P, K, 1), gen, spread=0.3)
+    act = (torch.rand(B, P, K, generator=gen) < 0.85).float()
+    act[:, :, 0] = 1.0
+    lrfs = lrfs * act.view(B, P, K, 1, 1)
+    if B * P > 1:
+        act[-1, -1] = 0
+        lrfs[-1, -1] = 0  # a patch with nothing in it: pose 0, agreement 0
+    xrot = torch.randn(B, P, K, 1, 3, generator=gen)
+    W1, b1 = torch.randn(O, 3, generator=gen) * 0.5, torch.randn(O, generator=gen) * 0.5
+    W2, b2 = torch.randn(4 * O, O, generator=gen) / O ** 0.5, torch.randn(4 * O, generator=gen) * 0.3
+    b2 = b2 + torch.tensor([2.0, 0.3, -0.4, 0.5]).repeat_interleave(O)  # a dominant mean transform: clustered votes
+    alpha, beta = torch.tensor([1.1]), torch.tensor([0.9])
+    Gp = torch.randn(B, P, O, 4, generator=gen)
+    Ga = torch.randn(B, P, O, generator=gen)
+
+    def run_oracle(dt):
+        ps = [t.clone().to(dt).requires_grad_(True) for t in (W1, b1, W2, b2, alpha, beta)]
+        t_raw = orc.transform_quats(xrot.to(dt), ps[0], ps[1], ps[2], ps[3])
+        v = orc.votes_from(lrfs.to(dt), t_raw)
+        pose_o, agr_o = orc.routing(v, act.to(dt), ps[4], ps[5], T)
+        ((pose_o * Gp.to(dt)).sum() + (agr_o * Ga.to(dt)).sum()).backward()
+        return [pose_o.detach(), agr_o.detach()] + [p.grad for p in ps]
+
+    ref = run_oracle(torch.float64)
+    r32 = run_oracle(torch.float32)
+    ps = [t.to(dev).requires_grad_(True) for t in (W1, b1, W2, b2, alpha, beta)]
+    Wc = ps[2] @ ps[0]
+    bc = torch.addmv(ps[3], ps[2], ps[1])
+    pose, agr = QF.routing_small(xrot.to(dev), lrfs.to(dev), act.to(dev), Wc, bc, ps[4], ps[5], T)
+    assert quat_err(pose.cpu(), ref[0]) < TOL
+    assert max_err(agr.cpu(), ref[1]) < TOL
+    if B * P > 1:
+        assert float(pose[-1, -1].abs().max()) == 0.0 and float(agr[-1, -1].abs().max()) == 0.0
+    ((pose * Gp.to(dev)).sum() + (agr * Ga.to(dev)).sum()).backward()
+    for k, p in enumerate(ps):
+        tol = max(TOL, 3.0 * rel_err(r32[k + 2], ref[k + 2]))
+        e = rel_err(p.grad.cpu(), ref[k + 2])
+        print("small margin k=%d err=%.2e tol=%.2e" % (k, e, tol))
+        assert e < tol, (k, e, tol)

@@ -47,6 +47,7 @@ def grads_close(named_grads, ref_grads, tol):
         ref = ref_grads[k]
         denom = max(float(ref.double().abs().max()), 0.25 * scale, 1e-30)
         e = max_err(g, ref) / denom
+        print("grad margin %s err=%.2e tol=%.2e" % (k, e, tol))
         if not e < tol:
             bad.append((k, e))
     return bad
