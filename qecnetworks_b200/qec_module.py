@@ -17,15 +17,58 @@ from torch.nn import Linear, Module, Parameter
 from . import functional as QF
 
 
+def _tf32_round(x):
+    """round-to-nearest onto the TF32 grid (10-bit mantissa); the result is exactly representable"""
+    return ((x.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+class _SplitTf32Matmul(torch.autograd.Function):
+    """y = xa @ wa^T in FP32 accuracy on the TF32 tensor cores (cuBLAS).
+
+    Both operands are split x = hi + lo with hi, lo on the TF32 grid (exact inputs for the tensor
+    cores) and the three significant products are ONE GEMM over a concatenated contraction axis:
+        [x_hi | x_hi | x_lo] @ [w_hi | w_lo | w_hi]^T = x_hi w_hi + x_hi w_lo + x_lo w_hi
+    accumulated in FP32; the dropped lo*lo term and the rounding of lo are ~2^-22 relative.
+    Measured on B200 for [8192,41] x [41,20480]: 122 us vs 466 us for the SIMT SGEMM (which is
+    bound by its 1.4 TB/s output path, not by FLOPs), max error 9e-7 of the largest entry vs
+    3e-7 for SGEMM.  The backward stays plain FP32 SGEMM."""
+
+    @staticmethod
+    def forward(ctx, xa, wa):
+        ctx.save_for_backward(xa, wa)
+        K = xa.shape[1]
+        pad = (-3 * K) % 16  # tensor-core kernels need an aligned contraction length
+        xh = _tf32_round(xa)
+        xl = _tf32_round(xa - xh)
+        wh = _tf32_round(wa)
+        wl = _tf32_round(wa - wh)
+        A = torch.cat([xh, xh, xl, xa.new_zeros(xa.shape[0], pad)], dim=1)
+        Bm = torch.cat([wh, wl, wh, wa.new_zeros(wa.shape[0], pad)], dim=1)
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            y = A @ Bm.t()
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        xa, wa = ctx.saved_tensors
+        g_xa = g @ wa if ctx.needs_input_grad[0] else None
+        g_wa = g.t() @ xa if ctx.needs_input_grad[1] else None
+        return g_xa, g_wa
+
+
 def _linear_bias_in_gemm(x, weight, bias, row_perm=None):
     """y = [x, 1] @ [W, b]^T.  Same value as F.linear(x, W, b), but the bias rides inside the
-    SGEMM (K+1) instead of a separate epilogue pass over the 671 MB output, and its gradient
+    GEMM (K+1) instead of a separate epilogue pass over the 671 MB output, and its gradient
     falls out of the weight-gradient GEMM instead of a separate 671 MB reduction."""
     xa = torch.cat([x, x.new_ones(x.shape[0], 1)], dim=1)
     wa = torch.cat([weight, bias.unsqueeze(1)], dim=1)
     if row_perm is not None:
         wa = wa.index_select(0, row_perm)  # output features re-ordered for free inside the GEMM
-    return xa @ wa.t()
+    return _SplitTf32Matmul.apply(xa, wa)
 
 
 class QecModule(Module):
