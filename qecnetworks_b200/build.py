@@ -19,7 +19,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-ftz=true", "-std=c++17",
     "-Xcompiler", "-fPIC",
-]
+] + os.environ.get("QEC_NVCC_EXTRA", "").split()
 
 
 def sources():

@@ -35,7 +35,6 @@ namespace cg = cooperative_groups;
 namespace qec {
 
 constexpr int kFT = 512;      // threads per CTA
-constexpr int kFW = kFT / 32;
 constexpr int kJcMax = 4096;  // resident votes per CTA
 constexpr int kTB = 3;        // routing iterations the cached backward supports
 
@@ -57,8 +56,9 @@ __device__ __forceinline__ float warp_reduce_scatter16(float (&a)[16], int lane)
     return a[0] + __shfl_xor_sync(0xffffffffu, a[0], 1);
 }
 
-template <int CL>
+template <int CL, int NT = kFT>
 struct ClusterReducer {
+    static constexpr int kFW = NT / 32;
     float* scratch;  // [16][kFW] warp partials
     float* part;     // [2][16] this CTA's published partial sums (double-buffered across sweeps)
     float* out;      // [16] solve result broadcast inside the CTA
@@ -118,7 +118,7 @@ struct ClusterReducer {
 
 __device__ __forceinline__ float ldg_stream_f32(const float* p) {
     float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));  // not volatile: schedulable
     return v;
 }
 __device__ __forceinline__ void red_add_q(float* p, Quat q) {  // REDG.E.ADD.F32x4
@@ -133,14 +133,19 @@ __device__ __forceinline__ void sts_q(float4* p, Quat q) { *p = make_float4(q.w,
 
 // walks this thread's votes jl = tid, tid + kFT, ... of the CTA's slice, tracking (k, i) of
 // j = j_begin + jl = k*I + i without a division per vote
-struct VoteWalker {
+template <int NT>
+struct VoteWalkerT {
     int k, i, dk, di, I;
-    __device__ __forceinline__ VoteWalker(int j_begin, int I_) : I(I_) {
-        const int j = j_begin + threadIdx.x;
+    __device__ __forceinline__ VoteWalkerT(int j_begin, int I_, int skip = 0) : I(I_) {
+        const int j = j_begin + threadIdx.x + skip;
         k = j / I;
         i = j - k * I;
-        dk = kFT / I;
-        di = kFT - dk * I;
+        dk = NT / I;
+        di = NT - dk * I;
+    }
+    __device__ __forceinline__ void next2() {  // advance by two strides
+        next();
+        next();
     }
     __device__ __forceinline__ void next() {
         i += di;
@@ -151,6 +156,7 @@ struct VoteWalker {
         }
     }
 };
+using VoteWalker = VoteWalkerT<kFT>;
 
 __device__ __forceinline__ Quat solve_pose(const float* acc, bool valid) {
     const Sym4 m = acc_to_sym(acc, 1.f / fmaxf(acc[10], 1e-12f));  // F.normalize(p=1) of the weights
@@ -194,6 +200,7 @@ __global__ void __launch_bounds__(kFT, 2)
         {
             VoteWalker w(j_begin, I);
             const float* tbase = t_oqi + (size_t)o * 4 * I;
+#pragma unroll 2
             for (int jl = threadIdx.x; jl < nloc; jl += kFT) {
                 const size_t row = (size_t)bp * K + w.k;
                 const float* tp = tbase + row * trow + w.i;
@@ -268,23 +275,31 @@ __global__ void __launch_bounds__(kFT, 2)
 }
 
 // ------------------------------------------------------------------------------------
-// backward (T <= kTB).  Levels t = T-1..0; sweep k completes level T-k (its adjoint vector u is
-// known from the previous reduction) and accumulates level T-k-1.  Per-vote quantities of the
-// forward chain (x^t = <pose^t, v>, 1 - d^t) are computed once in sweep 0 and cached in shared
-// memory; g_b of the last completed level and the running activation gradient are carried in
-// shared memory as well.  See routing_core.cuh for the algebra.
+// backward (T <= kTB = 3).  Levels t = T-1..0; sweep k completes level TT = T-k (its adjoint
+// vector u^TT is known from the previous reduction) and accumulates level TT-1.
+//
+// 256 threads x 16 resident votes per thread, two CTAs per SM (two capsules in flight per SM:
+// one capsule's reduce / Cholesky latency hides behind the other's sweep).  Shared memory per
+// vote: the vote (16 B) and the cached 1 - d^t of the levels below the top (8 B).  Everything
+// else is recomputed per sweep from per-capsule registers (T poses, T adjoint vectors): the
+// gradient w.r.t. b at level TT is rebuilt by walking down from the top level with two dot
+// products per level, which is cheaper than keeping it in shared memory and lets the second
+// CTA fit.  Two votes are processed per loop iteration with all loads issued first (ILP 2).
+// See routing_core.cuh for the algebra.
 // ------------------------------------------------------------------------------------
-struct BwdSmem {
-    float4* sv;
-    float* sx[kTB];
-    float* som[kTB];
-    float* sgb;
-    float* sga;
+constexpr int kBT = 256;
+
+struct BwdCaps {  // per-capsule state, registers
+    Quat ph[kTB], uh[kTB];
+    float rS[kTB];
+    float gsn;
 };
 
-struct BwdSweepArgs {
-    BwdSmem sm;
-    int nloc, j_begin, I, K;
+struct BwdGeom {
+    const float4* sv;
+    const float* som0;
+    const float* som1;
+    int nloc, I, K;
     long long bp;
     size_t trow;
     const float* act;
@@ -293,74 +308,149 @@ struct BwdSweepArgs {
     float* gtbase;
     float* g_lrfs;     // nullable
     float* g_act_row;  // nullable: no activation gradient -> only the top level is processed
-    Quat ut, pt;       // adjoint vector and pose of the level being completed
-    float rst, gsn;
 };
 
-// One backward sweep over this CTA's resident votes: completes level TT (TOP: TT = T-1, the
-// level whose votes are not detached -> writes dL/dt_raw, dL/dlrf) and accumulates level TT-1.
-template <int TT, bool TOP>
-__device__ __forceinline__ void bwd_sweep(const BwdSweepArgs& A, float (&acc)[15]) {
-    const bool chain = A.g_act_row != nullptr;
-    const bool more = chain && TT >= 1;
-    const bool last = chain && TT == 0;
-    const int I = A.I;
-    VoteWalker w(A.j_begin, I);
-    for (int jl = threadIdx.x; jl < A.nloc; jl += kFT) {
-        const Quat v = lds_q(A.sm.sv + jl);
-        const size_t row = (size_t)A.bp * A.K + w.k;
-        const float a = __ldg(A.act + row * I + w.i);
-        // b^TT and b^{TT-1} from the cached (1 - d) chain: b^{t+1} = b^t a (1 - d^t)
-        float b = a, blow = a;
-        if (TT >= 1) b = a * (a * A.sm.som[0][jl]);
-        if (TT >= 2) {
-            blow = b;
-            b = b * (a * A.sm.som[1][jl]);
-        }
-        const float x_t = A.sm.sx[TT][jl];
-        const float om_t = A.sm.som[TT][jl];
-        const float uv = qdot(A.ut, v);
-        float gb, ga;
-        if (TOP) {
-            gb = A.gsn * om_t;
-            ga = 0.f;
-            const float gx = -A.gsn * b * dist_grad(x_t);
-            const float wh = b * A.rst;
-            Quat gv = qscale(A.pt, fmaf(wh, uv, gx));  // p (gx + w <u,v>)
-            gv = qfma(wh * x_t, A.ut, gv);             // + u w <p,v>
-            const float* tp = A.tbase + row * A.trow + w.i;
-            const Quat traw = qmake(__ldg(tp), __ldg(tp + I), __ldg(tp + 2 * I), __ldg(tp + 3 * I));
-            const Quat lrf = ldq_nc(A.lrfs + (row * I + w.i) * 4);
-            const VoteParts vp = make_vote(lrf, traw);
-            Quat gt, gl;
-            vote_bwd(lrf, vp, gv, gt, gl);
-            float* gp = A.gtbase + row * A.trow + w.i;
-            gp[0] = gt.w; gp[I] = gt.x; gp[2 * I] = gt.y; gp[3 * I] = gt.z;
-            if (A.g_lrfs != nullptr) red_add_q(A.g_lrfs + (row * I + w.i) * 4, gl);  // sum over the O capsules
+// gradient w.r.t. b^TT (gb), running activation gradient (ga), and b^t for all levels
+template <int T, int TT>
+__device__ __forceinline__ void complete_levels(const BwdCaps& C, Quat v, float a, float om0, float om1, float& gb,
+                                                float& ga, float& x_tt, float& uv_tt, float (&b)[kTB]) {
+    b[0] = a;
+    b[1] = a * (a * om0);
+    b[2] = b[1] * (a * om1);
+    gb = 0.f;
+    ga = 0.f;
+#pragma unroll
+    for (int t = T - 1; t >= TT; --t) {
+        const float x = qdot(C.ph[t], v);
+        const float uv = qdot(C.uh[t], v);
+        float direct;
+        if (t == T - 1) {
+            direct = C.gsn * one_minus_dist(x);
         } else {
-            const float gprev = A.sm.sgb[jl];            // dL/db^{TT+1}
-            ga = fmaf(gprev * b, om_t, A.sm.sga[jl]);    // b^{TT+1} = b^TT a (1 - d^TT)
-            gb = gprev * a * om_t;
+            const float om = (t == 0) ? om0 : om1;  // cached 1 - d^t
+            ga = fmaf(gb * b[t], om, ga);           // b^{t+1} = b^t a (1 - d^t)
+            direct = gb * a * om;
         }
-        if (a != 0.f) gb = fmaf(uv * x_t, A.rst, gb);  // the M-path is gated by mask = [a != 0]
-        if (more) {
-            A.sm.sgb[jl] = gb;
-            A.sm.sga[jl] = ga;
-            // level TT-1: dL/dd_j = -g_b^TT b^{TT-1} a
-            const float x_l = A.sm.sx[TT >= 1 ? TT - 1 : 0][jl];
-            const float gx = -gb * blow * a * dist_grad(x_l);
-            acc[0] = fmaf(gx, v.w, acc[0]); acc[1] = fmaf(gx, v.x, acc[1]);
-            acc[2] = fmaf(gx, v.y, acc[2]); acc[3] = fmaf(gx, v.z, acc[3]);
-            acc_rank1(acc + 4, blow, v);
-            acc[14] += fabsf(blow);
+        gb = (a != 0.f) ? fmaf(uv * x, C.rS[t], direct) : direct;  // the M-path is gated by [a != 0]
+        if (t == TT) {
+            x_tt = x;
+            uv_tt = uv;
         }
-        if (last) atomicAdd(A.g_act_row + jl, ga + gb);  // + dL/db^0 (b^0 = a)
+    }
+}
+
+struct VoteIn {  // everything a sweep loads for one vote
+    Quat v;
+    float a, om0, om1;
+    Quat traw, lrf;  // only in the top sweep
+};
+
+template <int T, int TT>
+__device__ __forceinline__ VoteIn bwd_load(const BwdGeom& G, int jl, const VoteWalkerT<kBT>& w) {
+    VoteIn in;
+    in.v = lds_q(G.sv + jl);
+    const size_t row = (size_t)G.bp * G.K + w.k;
+    in.a = __ldg(G.act + row * G.I + w.i);
+    in.om0 = (T >= 2) ? G.som0[jl] : 1.f;
+    in.om1 = (T >= 3) ? G.som1[jl] : 1.f;
+    if (TT == T - 1) {
+        const float* tp = G.tbase + row * G.trow + w.i;
+        const int I = G.I;
+        in.traw = qmake(__ldg(tp), __ldg(tp + I), __ldg(tp + 2 * I), __ldg(tp + 3 * I));
+        in.lrf = ldq_nc(G.lrfs + (row * I + w.i) * 4);
+    }
+    return in;
+}
+
+template <int T, int TT>
+__device__ __forceinline__ void bwd_vote(const BwdGeom& G, const BwdCaps& C, const VoteIn& in, int jl,
+                                         const VoteWalkerT<kBT>& w, float (&acc)[15]) {
+    const bool chain = G.g_act_row != nullptr;
+    float gb, ga, x, uv, b[kTB];
+    complete_levels<T, TT>(C, in.v, in.a, in.om0, in.om1, gb, ga, x, uv, b);
+    if (TT == T - 1) {  // the level whose votes are not detached: dL/dvote -> dL/dt_raw, dL/dlrf
+        const float gx = -C.gsn * b[TT] * dist_grad(x);
+        const float wh = b[TT] * C.rS[TT];
+        Quat gv = qscale(C.ph[TT], fmaf(wh, uv, gx));  // p (gx + w <u,v>)
+        gv = qfma(wh * x, C.uh[TT], gv);               // + u w <p,v>
+        const VoteParts vp = make_vote(in.lrf, in.traw);
+        Quat gt, gl;
+        vote_bwd(in.lrf, vp, gv, gt, gl);
+        const size_t row = (size_t)G.bp * G.K + w.k;
+        float* gp = G.gtbase + row * G.trow + w.i;
+        const int I = G.I;
+        gp[0] = gt.w; gp[I] = gt.x; gp[2 * I] = gt.y; gp[3 * I] = gt.z;
+        if (G.g_lrfs != nullptr) red_add_q(G.g_lrfs + (row * I + w.i) * 4, gl);  // sum over the O capsules
+    }
+    if (TT >= 1 && chain) {  // level TT-1: dL/dd_j = -g_b^TT b^{TT-1} a
+        const float xl = qdot(C.ph[TT >= 1 ? TT - 1 : 0], in.v);
+        const float bl = b[TT >= 1 ? TT - 1 : 0];
+        const float gx = -gb * bl * in.a * dist_grad(xl);
+        acc[0] = fmaf(gx, in.v.w, acc[0]); acc[1] = fmaf(gx, in.v.x, acc[1]);
+        acc[2] = fmaf(gx, in.v.y, acc[2]); acc[3] = fmaf(gx, in.v.z, acc[3]);
+        acc_rank1(acc + 4, bl, in.v);
+        acc[14] += fabsf(bl);
+    }
+    if (TT == 0 && chain) atomicAdd(G.g_act_row + jl, ga + gb);  // + dL/db^0 (b^0 = a)
+}
+
+template <int T, int TT>
+__device__ __forceinline__ void bwd_sweep(const BwdGeom& G, const BwdCaps& C, int j_begin, float (&acc)[15]) {
+    VoteWalkerT<kBT> w0(j_begin, G.I), w1(j_begin, G.I, kBT);
+    int jl = threadIdx.x;
+    for (; jl + kBT < G.nloc; jl += 2 * kBT) {  // two votes per iteration, loads first
+        const VoteIn i0 = bwd_load<T, TT>(G, jl, w0);
+        const VoteIn i1 = bwd_load<T, TT>(G, jl + kBT, w1);
+        bwd_vote<T, TT>(G, C, i0, jl, w0, acc);
+        bwd_vote<T, TT>(G, C, i1, jl + kBT, w1, acc);
+        w0.next2();
+        w1.next2();
+    }
+    if (jl < G.nloc) {
+        const VoteIn i0 = bwd_load<T, TT>(G, jl, w0);
+        bwd_vote<T, TT>(G, C, i0, jl, w0, acc);
+    }
+}
+
+// sweep 0: generate the votes, cache 1 - d^t of the levels below the top, accumulate level T-1
+template <int T>
+__device__ __forceinline__ void bwd_sweep0(const BwdGeom& G, const BwdCaps& C, int j_begin, float4* sv, float* som0,
+                                           float* som1, float (&acc)[15]) {
+    VoteWalkerT<kBT> w(j_begin, G.I);
+    const int I = G.I;
+#pragma unroll 2
+    for (int jl = threadIdx.x; jl < G.nloc; jl += kBT) {
+        const size_t row = (size_t)G.bp * G.K + w.k;
+        const float* tp = G.tbase + row * G.trow + w.i;
+        const Quat traw = qmake(ldg_stream_f32(tp), ldg_stream_f32(tp + I), ldg_stream_f32(tp + 2 * I),
+                                ldg_stream_f32(tp + 3 * I));
+        const Quat lrf = ldq_nc(G.lrfs + (row * I + w.i) * 4);
+        const float a = __ldg(G.act + row * I + w.i);
+        const Quat v = make_vote(lrf, traw).vote;
+        sts_q(sv + jl, v);
+        float b = a;
+        if (T >= 2) {
+            const float om = one_minus_dist(qdot(C.ph[0], v));
+            som0[jl] = om;
+            b *= a * om;
+        }
+        if (T >= 3) {
+            const float om = one_minus_dist(qdot(C.ph[1], v));
+            som1[jl] = om;
+            b *= a * om;
+        }
+        // level T-1 (final distance): dL/dd_j = -gsn b^{T-1}_j
+        const float gx = -C.gsn * b * dist_grad(qdot(C.ph[T - 1], v));
+        acc[0] = fmaf(gx, v.w, acc[0]); acc[1] = fmaf(gx, v.x, acc[1]);
+        acc[2] = fmaf(gx, v.y, acc[2]); acc[3] = fmaf(gx, v.z, acc[3]);
+        acc_rank1(acc + 4, b, v);
+        acc[14] += fabsf(b);
         w.next();
     }
 }
 
 template <int CL>
-__global__ void __launch_bounds__(kFT, 1)
+__global__ void __launch_bounds__(kBT, 2)
     routing_fused_bwd_kernel(const float* __restrict__ t_oqi, const float* __restrict__ lrfs,
                              const float* __restrict__ act, const float* __restrict__ alpha_p,
                              const float* __restrict__ beta_p, const float* __restrict__ poses_all,
@@ -368,17 +458,10 @@ __global__ void __launch_bounds__(kFT, 1)
                              const float* __restrict__ g_agr, float* __restrict__ g_toqi, float* g_lrfs, float* g_act,
                              float* g_alpha_beta, long long Nc, int K, int I, int O, int T) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    BwdSmem sm;
-    sm.sv = reinterpret_cast<float4*>(smem_raw);
-    float* f = reinterpret_cast<float*>(sm.sv + kJcMax);
-#pragma unroll
-    for (int t = 0; t < kTB; ++t) {
-        sm.sx[t] = f + (2 * t) * kJcMax;
-        sm.som[t] = f + (2 * t + 1) * kJcMax;
-    }
-    sm.sgb = f + 2 * kTB * kJcMax;
-    sm.sga = sm.sgb + kJcMax;
-    ClusterReducer<CL> red(sm.sga + kJcMax);
+    float4* sv = reinterpret_cast<float4*>(smem_raw);
+    float* som0 = reinterpret_cast<float*>(sv + kJcMax);
+    float* som1 = som0 + kJcMax;
+    ClusterReducer<CL, kBT> red(som1 + kJcMax);
     int rank = 0;
     if (CL > 1) rank = (int)cg::this_cluster().block_rank();
     const long long cid = blockIdx.x / CL, ncl = gridDim.x / CL;
@@ -387,23 +470,26 @@ __global__ void __launch_bounds__(kFT, 1)
     const int j_begin = min(J, rank * Jc);
     const int nloc = min(J, j_begin + Jc) - j_begin;
     const float alpha = __ldg(alpha_p), beta = __ldg(beta_p);
-    const size_t trow = (size_t)4 * I * O;
     const bool need_chain = g_act != nullptr;
     float ga_tot = 0.f, gb_tot = 0.f;
 
     for (long long c = cid; c < Nc; c += ncl) {
         const long long bp = c / O;
         const int o = (int)(c - bp * O);
-        const float* tbase = t_oqi + (size_t)o * 4 * I;
-        float* gtbase = g_toqi + (size_t)o * 4 * I;
-        // per-capsule scalars
-        Quat ph[kTB], uh[kTB];
-        float rS[kTB];
+        BwdGeom G;
+        G.sv = sv; G.som0 = som0; G.som1 = som1; G.nloc = nloc; G.I = I; G.K = K; G.bp = bp;
+        G.trow = (size_t)4 * I * O;
+        G.act = act; G.lrfs = lrfs;
+        G.tbase = t_oqi + (size_t)o * 4 * I;
+        G.gtbase = g_toqi + (size_t)o * 4 * I;
+        G.g_lrfs = g_lrfs;
+        G.g_act_row = need_chain ? g_act + (size_t)bp * J + j_begin : nullptr;
+        BwdCaps C;
 #pragma unroll
         for (int t = 0; t < kTB; ++t) {
-            ph[t] = (t < T) ? ldq_nc(poses_all + ((size_t)t * Nc + c) * 4) : qmake(0.f, 0.f, 0.f, 0.f);
-            uh[t] = qmake(0.f, 0.f, 0.f, 0.f);
-            rS[t] = 0.f;
+            C.ph[t] = (t < T) ? ldq_nc(poses_all + ((size_t)t * Nc + c) * 4) : qmake(0.f, 0.f, 0.f, 0.f);
+            C.uh[t] = qmake(0.f, 0.f, 0.f, 0.f);
+            C.rS[t] = 0.f;
         }
         const float s = __ldg(stats + 2 * c), n = __ldg(stats + 2 * c + 1);
         const bool has = n > 0.f;
@@ -411,57 +497,25 @@ __global__ void __launch_bounds__(kFT, 1)
         const float gz = has ? __ldg(g_agr + c) * sg * (1.f - sg) : 0.f;
         ga_tot += gz * s;
         gb_tot += gz;
-        const float gsn = has ? gz * alpha / n : 0.f;
+        C.gsn = has ? gz * alpha / n : 0.f;
         const Quat gpose = ldq_nc(g_pose + (size_t)c * 4);
 
-        // ---- sweep 0: generate votes, forward chain (cached), accumulate level T-1 -----------
         float acc[15];
         zero_acc(acc);
-        {
-            VoteWalker w(j_begin, I);
-            for (int jl = threadIdx.x; jl < nloc; jl += kFT) {
-                const size_t row = (size_t)bp * K + w.k;
-                const float* tp = tbase + row * trow + w.i;
-                const Quat traw = qmake(ldg_stream_f32(tp), ldg_stream_f32(tp + I), ldg_stream_f32(tp + 2 * I),
-                                        ldg_stream_f32(tp + 3 * I));
-                const Quat lrf = ldq_nc(lrfs + (row * I + w.i) * 4);
-                const float a = __ldg(act + row * I + w.i);
-                const Quat v = make_vote(lrf, traw).vote;
-                sts_q(sm.sv + jl, v);
-                float b = a, xl = 0.f, bl = 0.f;
-#pragma unroll
-                for (int t = 0; t < kTB; ++t) {
-                    if (t < T) {
-                        const float x = qdot(ph[t], v);
-                        const float om = one_minus_dist(x);
-                        sm.sx[t][jl] = x;
-                        sm.som[t][jl] = om;
-                        xl = x;
-                        bl = b;  // b^t
-                        b *= a * om;
-                    }
-                }
-                // level T-1 (final distance): dL/dd_j = -gsn b^{T-1}_j
-                const float gx = -gsn * bl * dist_grad(xl);
-                acc[0] = fmaf(gx, v.w, acc[0]); acc[1] = fmaf(gx, v.x, acc[1]);
-                acc[2] = fmaf(gx, v.y, acc[2]); acc[3] = fmaf(gx, v.z, acc[3]);
-                acc_rank1(acc + 4, bl, v);
-                acc[14] += fabsf(bl);
-                w.next();
-            }
-        }
-        // ---- sweeps k = 1..: complete level t = T-k, accumulate level t-1 -------------------
+        if (T == 3) bwd_sweep0<3>(G, C, j_begin, sv, som0, som1, acc);
+        else if (T == 2) bwd_sweep0<2>(G, C, j_begin, sv, som0, som1, acc);
+        else bwd_sweep0<1>(G, C, j_begin, sv, som0, som1, acc);
+
         const int nsweeps = need_chain ? T : 1;
         for (int k = 1; k <= nsweeps; ++k) {
             const int t = T - k;  // level being completed
-            // solve u^t from the reduction of the previous sweep
-            red.reduce(acc);
+            red.reduce(acc);      // sums of the level accumulated by the previous sweep
             float r[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
             if (red.solver()) {
-                Quat p = ph[0];
+                Quat p = C.ph[0];
 #pragma unroll
                 for (int u = 1; u < kTB; ++u)
-                    if (u == t) p = ph[u];
+                    if (u == t) p = C.ph[u];
                 const float rs = 1.f / fmaxf(acc[14], 1e-12f);
                 const Sym4 m = acc_to_sym(acc + 4, rs);
                 Quat gp = qmake(acc[0], acc[1], acc[2], acc[3]);
@@ -472,19 +526,26 @@ __global__ void __launch_bounds__(kFT, 1)
                 r[0] = u.w; r[1] = u.x; r[2] = u.y; r[3] = u.z; r[4] = rs;
             }
             red.bcast(r);
-            BwdSweepArgs a;
-            a.sm = sm; a.nloc = nloc; a.j_begin = j_begin; a.I = I; a.K = K; a.bp = bp; a.trow = trow;
-            a.act = act; a.lrfs = lrfs; a.tbase = tbase; a.gtbase = gtbase; a.g_lrfs = g_lrfs;
-            a.g_act_row = need_chain ? g_act + (size_t)bp * J + j_begin : nullptr;
-            a.ut = qmake(r[0], r[1], r[2], r[3]); a.rst = r[4]; a.gsn = gsn;
+#pragma unroll
+            for (int u = 0; u < kTB; ++u)
+                if (u == t) {
+                    C.uh[u] = qmake(r[0], r[1], r[2], r[3]);
+                    C.rS[u] = r[4];
+                }
             zero_acc(acc);
-            const bool top = (k == 1);
-            // the level index is a template parameter: the (1-d) chain, the cached loads and the
-            // top-level vote-gradient code fold at compile time
-            if (t == 2) { a.pt = ph[2]; bwd_sweep<2, true>(a, acc); }
-            else if (t == 1) { a.pt = ph[1]; if (top) bwd_sweep<1, true>(a, acc); else bwd_sweep<1, false>(a, acc); }
-            else { a.pt = ph[0]; if (top) bwd_sweep<0, true>(a, acc); else bwd_sweep<0, false>(a, acc); }
+            // total iterations and level are template parameters: the chain walk, the cached loads
+            // and the top-level vote-gradient code fold at compile time
+            switch (T * 4 + t) {
+                case 3 * 4 + 2: bwd_sweep<3, 2>(G, C, j_begin, acc); break;
+                case 3 * 4 + 1: bwd_sweep<3, 1>(G, C, j_begin, acc); break;
+                case 3 * 4 + 0: bwd_sweep<3, 0>(G, C, j_begin, acc); break;
+                case 2 * 4 + 1: bwd_sweep<2, 1>(G, C, j_begin, acc); break;
+                case 2 * 4 + 0: bwd_sweep<2, 0>(G, C, j_begin, acc); break;
+                default: bwd_sweep<1, 0>(G, C, j_begin, acc); break;
+            }
         }
+        // the next capsule's sweep 0 overwrites this thread's own slots only; the reducer's
+        // scratch is protected by the barriers inside reduce()
     }
     if (rank == 0 && threadIdx.x == 0) {
         atomicAdd(g_alpha_beta, ga_tot);
@@ -493,15 +554,15 @@ __global__ void __launch_bounds__(kFT, 1)
     if (CL > 1) cg::this_cluster().sync();
 }
 
-constexpr size_t kRedBytes = sizeof(float) * (16 * kFW + 48);
+constexpr size_t kRedBytes = sizeof(float) * (16 * (kFT / 32) + 48);  // sized for the wider CTA
 constexpr size_t kFwdSmem = (sizeof(float4) + sizeof(float2)) * kJcMax + kRedBytes;
-constexpr size_t kBwdSmem = (sizeof(float4) + sizeof(float) * (2 * kTB + 2)) * kJcMax + kRedBytes;
+constexpr size_t kBwdSmem = (sizeof(float4) + sizeof(float) * (kTB - 1)) * kJcMax + kRedBytes;
 
 // persistent grid: as many clusters as can be co-resident, never more than there are capsules
 template <class Kern>
-static int fused_grid(Kern kern, int CL, size_t smem, long long Nc, cudaLaunchConfig_t& cfg,
+static int fused_grid(Kern kern, int CL, int threads, size_t smem, long long Nc, cudaLaunchConfig_t& cfg,
                       cudaLaunchAttribute* attr, int& cached_clusters) {
-    cfg.blockDim = dim3(kFT);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.numAttrs = 0;
     cfg.attrs = attr;
@@ -517,12 +578,12 @@ static int fused_grid(Kern kern, int CL, size_t smem, long long Nc, cudaLaunchCo
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         if (CL > 1) {
-            cfg.gridDim = dim3(CL * 2 * kNumSMs);  // upper bound for the occupancy query
+            cfg.gridDim = dim3(CL * 4 * kNumSMs);  // upper bound for the occupancy query
             e = cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg);
             if (e != cudaSuccess) return (int)e;
         } else {
             int per_sm = 0;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFT, smem);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
             if (e != cudaSuccess) return (int)e;
             clusters = per_sm * kNumSMs;
         }
@@ -548,7 +609,7 @@ static int launch_fused_fwd(const float* t_oqi, const float* lrfs, const float* 
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     static int cached = -1;
-    const int rc = fused_grid(kern, CL, kFwdSmem, Nc, cfg, attr, cached);
+    const int rc = fused_grid(kern, CL, kFT, kFwdSmem, Nc, cfg, attr, cached);
     if (rc) return rc;
     cfg.stream = st;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, t_oqi, lrfs, act, alpha, beta, pose, agreement, poses_all,
@@ -565,7 +626,7 @@ static int launch_fused_bwd(const float* t_oqi, const float* lrfs, const float* 
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     static int cached = -1;
-    const int rc = fused_grid(kern, CL, kBwdSmem, Nc, cfg, attr, cached);
+    const int rc = fused_grid(kern, CL, kBT, kBwdSmem, Nc, cfg, attr, cached);
     if (rc) return rc;
     cfg.stream = st;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, t_oqi, lrfs, act, alpha, beta, poses_all, stats, g_pose,
