@@ -110,7 +110,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -264,7 +264,7 @@ def run_b200(a):
             train_step(*static)
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
-    if not a.no_graph and world == 1:
+    if not a.no_graph:
         try:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
@@ -274,6 +274,11 @@ def run_b200(a):
                 sys.stderr.write("CUDA graph capture failed (%s); running eagerly\n" % (e,))
             graph = None
             torch.cuda.synchronize()
+        if world > 1:  # all ranks must agree, or the NCCL calls inside/outside the graphs would mismatch
+            ok = torch.tensor([1 if graph is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                graph = None
 
     def run_step(b, from_host=False):
         for s, t in zip(static, b):
@@ -327,7 +332,7 @@ def run_b200(a):
     kernels = []
     roofline = None
     fp32_peak = None
-    if rank == 0:
+    if True:  # every rank runs the pass (the step contains the gradient all-reduce); rank 0 reports
         fp32_peak = measure_fp32_peak(torch, _lib, dev)
         hbm_peak, peak_src = load_peaks()
         _lib.start_kernel_timing()
@@ -409,10 +414,16 @@ def run_b200(a):
             "kernels": kernels,
             "final_loss": last,
         }
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
+        # Tear-down of a process group whose communicator is still referenced by a captured CUDA
+        # graph can block for minutes; results are out, so synchronise and leave without it.
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -6,10 +6,15 @@ B200 box, gloo in the CPU tests).  Replaces the reference's nn.DataParallel
 The hot path shards over the batch with no data-path collective (every capsule
 depends on one sample only); the gradient all-reduce is the only
 exchange step."""
+import datetime
 import os
 
 import torch
 import torch.distributed as dist
+
+
+# a mismatched collective must fail in minutes, not hang a GPU box for the default 10
+_TIMEOUT = datetime.timedelta(seconds=int(os.environ.get("QEC_DIST_TIMEOUT_S", "120")))
 
 
 def init_from_env(backend=None):
@@ -25,9 +30,9 @@ def init_from_env(backend=None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+            dist.init_process_group(backend, device_id=torch.device("cuda", local), timeout=_TIMEOUT)
         else:
-            dist.init_process_group(backend)
+            dist.init_process_group(backend, timeout=_TIMEOUT)
     return rank, world, local
 
 

@@ -1,0 +1,51 @@
+"""GPU, needs >= 2 devices (skipped otherwise; run with `gpurun --gpus 2`): the data-parallel step over
+NCCL gives every rank the gradient of the GLOBAL-batch mean loss."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import qecnetworks_b200 as qb
+    from qecnetworks_b200 import ddp
+    from qecnetworks_b200.synthetic import synthetic_batch
+
+    ddp.init_from_env("nccl")
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(7)
+    net = qb.QecNet(2048, 16, 10, 3).to(dev)
+    ddp.broadcast_parameters(net, 0)
+    bucket = ddp.FlatGradBucket(net.parameters())
+    B = 4
+    points, lrfs, act, labels = [t.to(dev) for t in synthetic_batch(B * world, ncls=10, seed=11)]
+    lo, hi = ddp.shard_batch(B * world, rank, world)
+    bucket.zero()
+    _, a = net(points[lo:hi], lrfs[lo:hi], act[lo:hi], None)
+    net.spread_loss(a, labels[lo:hi]).backward()
+    bucket.all_reduce_mean()
+    got = bucket.flat.clone()
+    # the same global batch on one device
+    bucket.zero()
+    _, a = net(points, lrfs, act, None)
+    net.spread_loss(a, labels).backward()
+    ref = bucket.flat.clone()
+    err = float((got - ref).abs().max() / ref.abs().max())
+    out[rank] = err
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ddp_gradients_match_global_batch():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, 29731, out), nprocs=2, join=True)
+    assert out[0] < 1e-4 and out[1] < 1e-4, dict(out)
