@@ -36,8 +36,7 @@ __global__ void __launch_bounds__(kLT)
     }
     coop.reduce(acc);
     const Sym4 m = acc_to_sym(acc, 1.f / (float)K);
-    float lam;
-    Quat p = qfix(top_eigvec(m, lam, WarpDone()));
+    Quat p = qfix(top_eigvec_psd(m, WarpDone()));  // (1/K) sum q q^T is positive semi-definite
     if (!(acc[10] > 0.f)) p = qmake(0.f, 0.f, 0.f, 0.f);
     if (active && coop.leader()) stq(mean + (size_t)c * 4, p);
 }

@@ -54,7 +54,7 @@ __device__ __forceinline__ float routing_forward_capsule(const Coop& coop, const
 #pragma unroll
     for (int t = 0; t < TMAX; ++t) {
         if (t < T) {
-            float acc[12];  // M (10), S = sum |b|, sum of all vote components
+            float acc[13];  // M (10), S = sum |b|, sum of all vote components, sum b
             zero_acc(acc);
             for (int j = coop.first(); j < J; j += coop.stride()) {
                 const Quat v = votes.get(j);
@@ -64,6 +64,7 @@ __device__ __forceinline__ float routing_forward_capsule(const Coop& coop, const
                 for (int u = 0; u < TMAX; ++u)
                     if (u < t) b *= a * one_minus_dist(qdot(ph[u], v));
                 acc[10] += fabsf(b);
+                acc[12] += b;
                 acc_rank1(acc, b, v);
                 if (t == 0) acc[11] += (v.w + v.x) + (v.y + v.z);
             }
@@ -72,8 +73,8 @@ __device__ __forceinline__ float routing_forward_capsule(const Coop& coop, const
             if (coop.solver()) {
                 if (t == 0) valid = acc[11] != 0.f;  // reference qec_module.py:72-73
                 const Sym4 m = acc_to_sym(acc, 1.f / fmaxf(acc[10], 1e-12f));  // F.normalize(p=1)
-                float lam;
-                Quat p = qfix(top_eigvec(m, lam, WarpDone()));
+                // sum b == sum |b| bit-exactly (same values, same order) unless a weight is negative
+                Quat p = qfix(top_eigvec_weighted(m, acc[12] != acc[10], WarpDone()));
                 if (!valid) p = qmake(0.f, 0.f, 0.f, 0.f);
                 r[0] = p.w; r[1] = p.x; r[2] = p.y; r[3] = p.z;
             }

@@ -156,30 +156,34 @@ struct VoteWalkerT {
         }
     }
 };
-using VoteWalker = VoteWalkerT<kFT>;
 
+// acc: M (10), [10] = sum |b|, [11] = sum b
 __device__ __forceinline__ Quat solve_pose(const float* acc, bool valid) {
     const Sym4 m = acc_to_sym(acc, 1.f / fmaxf(acc[10], 1e-12f));  // F.normalize(p=1) of the weights
-    float lam;
-    Quat p = qfix(top_eigvec(m, lam, WarpDone()));
+    // sum b == sum |b| bit-exactly (same values, same order) unless a weight is negative
+    Quat p = qfix(top_eigvec_weighted(m, acc[11] != acc[10], WarpDone()));
     if (!valid) p = qmake(0.f, 0.f, 0.f, 0.f);
     return p;
 }
 
 // ------------------------------------------------------------------------------------
-// forward
+// forward.  256 threads x 16 resident votes per thread, two CTAs per SM; every sweep handles
+// two votes per loop iteration with the loads issued first (ILP 2).
 // ------------------------------------------------------------------------------------
+constexpr int kFwdT = 256;
+
 template <int CL>
-__global__ void __launch_bounds__(kFT, 2)
+__global__ void __launch_bounds__(kFwdT, 2)
     routing_fused_fwd_kernel(const float* __restrict__ t_oqi, const float* __restrict__ lrfs,
                              const float* __restrict__ act, const float* __restrict__ alpha_p,
                              const float* __restrict__ beta_p, float* __restrict__ pose,
                              float* __restrict__ agreement, float* __restrict__ poses_all,
                              float* __restrict__ stats, long long Nc, int K, int I, int O, int T) {
+    constexpr int NT = kFwdT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* sv = reinterpret_cast<float4*>(smem_raw);
-    float2* sab = reinterpret_cast<float2*>(sv + kJcMax);  // (activation, routing weight b)
-    ClusterReducer<CL> red(reinterpret_cast<float*>(sab + kJcMax));
+    float4* __restrict__ sv = reinterpret_cast<float4*>(smem_raw);
+    float2* __restrict__ sab = reinterpret_cast<float2*>(sv + kJcMax);  // (activation, routing weight b)
+    ClusterReducer<CL, NT> red(reinterpret_cast<float*>(sab + kJcMax));
     int rank = 0;
     if (CL > 1) rank = (int)cg::this_cluster().block_rank();
     const long long cid = blockIdx.x / CL, ncl = gridDim.x / CL;
@@ -194,34 +198,48 @@ __global__ void __launch_bounds__(kFT, 2)
     for (long long c = cid; c < Nc; c += ncl) {
         const long long bp = c / O;
         const int o = (int)(c - bp * O);
+        const float* tbase = t_oqi + (size_t)o * 4 * I;
         // ---- generate the votes (once) + sweep 0: M^0 = sum a v v^T, b^0 = a ----------------
-        float acc[12];
+        float acc[13];  // M (10), sum |a|, sum a, sum of all vote components
         zero_acc(acc);
         {
-            VoteWalker w(j_begin, I);
-            const float* tbase = t_oqi + (size_t)o * 4 * I;
-#pragma unroll 2
-            for (int jl = threadIdx.x; jl < nloc; jl += kFT) {
+            struct Raw { Quat traw, lrf; float a; };
+            auto load = [&](const VoteWalkerT<NT>& w) {
+                Raw r;
                 const size_t row = (size_t)bp * K + w.k;
                 const float* tp = tbase + row * trow + w.i;
-                const Quat traw = qmake(ldg_stream_f32(tp), ldg_stream_f32(tp + I), ldg_stream_f32(tp + 2 * I),
-                                        ldg_stream_f32(tp + 3 * I));
-                const Quat lrf = ldq_nc(lrfs + (row * I + w.i) * 4);
-                const float a = __ldg(act + row * I + w.i);
-                const Quat v = make_vote(lrf, traw).vote;
+                r.traw = qmake(ldg_stream_f32(tp), ldg_stream_f32(tp + I), ldg_stream_f32(tp + 2 * I),
+                               ldg_stream_f32(tp + 3 * I));
+                r.lrf = ldq_nc(lrfs + (row * I + w.i) * 4);
+                r.a = __ldg(act + row * I + w.i);
+                return r;
+            };
+            auto use = [&](const Raw& r, int jl) {
+                const Quat v = make_vote(r.lrf, r.traw).vote;
                 sts_q(sv + jl, v);
-                sab[jl] = make_float2(a, a);
-                acc[10] += fabsf(a);
-                acc_rank1(acc, a, v);
-                acc[11] += (v.w + v.x) + (v.y + v.z);
-                w.next();
+                sab[jl] = make_float2(r.a, r.a);
+                acc[10] += fabsf(r.a);
+                acc[11] += r.a;
+                acc_rank1(acc, r.a, v);
+                acc[12] += (v.w + v.x) + (v.y + v.z);
+            };
+            VoteWalkerT<NT> w0(j_begin, I), w1(j_begin, I, NT);
+            int jl = threadIdx.x;
+            for (; jl + NT < nloc; jl += 2 * NT) {
+                const Raw r0 = load(w0);
+                const Raw r1 = load(w1);
+                use(r0, jl);
+                use(r1, jl + NT);
+                w0.next2();
+                w1.next2();
             }
+            if (jl < nloc) use(load(w0), jl);
         }
         red.reduce(acc);
         bool valid = false;
         float r[4] = {0.f, 0.f, 0.f, 0.f};
         if (red.solver()) {
-            valid = acc[11] != 0.f;  // reference qec_module.py:72-73
+            valid = acc[12] != 0.f;  // reference qec_module.py:72-73
             const Quat p = solve_pose(acc, valid);
             r[0] = p.w; r[1] = p.x; r[2] = p.y; r[3] = p.z;
         }
@@ -230,17 +248,23 @@ __global__ void __launch_bounds__(kFT, 2)
         if (writer) stq(poses_all + (size_t)c * 4, p);
         // ---- sweeps 1..T-1: b <- b a (1 - d(pose, v)), M^t = sum b v v^T, all from shared memory
         for (int t = 1; t < T; ++t) {
-            float a2[11];
+            float a2[12];
             zero_acc(a2);
-#pragma unroll 2
-            for (int jl = threadIdx.x; jl < nloc; jl += kFT) {
-                const Quat v = lds_q(sv + jl);
-                const float2 ab = sab[jl];
+            auto step = [&](Quat v, float2 ab, int jl) {
                 const float b = ab.y * (ab.x * one_minus_dist(qdot(p, v)));
                 sab[jl].y = b;
                 a2[10] += fabsf(b);
+                a2[11] += b;
                 acc_rank1(a2, b, v);
+            };
+            int jl = threadIdx.x;
+            for (; jl + NT < nloc; jl += 2 * NT) {
+                const Quat v0 = lds_q(sv + jl), v1 = lds_q(sv + jl + NT);
+                const float2 ab0 = sab[jl], ab1 = sab[jl + NT];
+                step(v0, ab0, jl);
+                step(v1, ab1, jl + NT);
             }
+            if (jl < nloc) step(lds_q(sv + jl), sab[jl], jl);
             red.reduce(a2);
             if (red.solver()) {
                 const Quat q = solve_pose(a2, valid);
@@ -252,12 +276,19 @@ __global__ void __launch_bounds__(kFT, 2)
         }
         // ---- epilogue sweep: inlier score (reference qec_module.py:188-193) ---------------------
         float e[2] = {0.f, 0.f};
-#pragma unroll 2
-        for (int jl = threadIdx.x; jl < nloc; jl += kFT) {
-            const Quat v = lds_q(sv + jl);
-            const float b = sab[jl].y;
-            e[0] = fmaf(b, one_minus_dist(qdot(p, v)), e[0]);
-            e[1] += (b != 0.f) ? 1.f : 0.f;
+        {
+            auto fin = [&](Quat v, float b) {
+                e[0] = fmaf(b, one_minus_dist(qdot(p, v)), e[0]);
+                e[1] += (b != 0.f) ? 1.f : 0.f;
+            };
+            int jl = threadIdx.x;
+            for (; jl + NT < nloc; jl += 2 * NT) {
+                const Quat v0 = lds_q(sv + jl), v1 = lds_q(sv + jl + NT);
+                const float b0 = sab[jl].y, b1 = sab[jl + NT].y;
+                fin(v0, b0);
+                fin(v1, b1);
+            }
+            if (jl < nloc) fin(lds_q(sv + jl), sab[jl].y);
         }
         red.reduce(e);
         if (rank == 0 && threadIdx.x == 0) {
@@ -609,7 +640,7 @@ static int launch_fused_fwd(const float* t_oqi, const float* lrfs, const float* 
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     static int cached = -1;
-    const int rc = fused_grid(kern, CL, kFT, kFwdSmem, Nc, cfg, attr, cached);
+    const int rc = fused_grid(kern, CL, kFwdT, kFwdSmem, Nc, cfg, attr, cached);
     if (rc) return rc;
     cfg.stream = st;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, t_oqi, lrfs, act, alpha, beta, pose, agreement, poses_all,

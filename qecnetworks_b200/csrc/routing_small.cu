@@ -99,13 +99,14 @@ __global__ void __launch_bounds__(kST)
         stage_patch(st, xrot, lrfs, act, bp, K);
         Quat v[KMAX];
         float b[KMAX];
-        float acc[12];
+        float acc[13];  // M (10), sum |b|, sum of vote components, sum b
         zero_acc(acc);
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
             v[k] = make_vote(q_from(st.lrf[k]), cr.apply(st.x[k])).vote;
             b[k] = st.a[k];
             acc[10] += fabsf(b[k]);
+            acc[12] += b[k];
             acc_rank1(acc, b[k], v[k]);
             acc[11] += (v[k].w + v[k].x) + (v[k].y + v[k].z);
         }
@@ -114,8 +115,7 @@ __global__ void __launch_bounds__(kST)
         Quat p;
         for (int t = 0;; ++t) {
             const Sym4 m = acc_to_sym(acc, 1.f / fmaxf(acc[10], 1e-12f));
-            float lam;
-            p = qfix(top_eigvec(m, lam, WarpDone()));
+            p = qfix(top_eigvec_weighted(m, acc[12] != acc[10], WarpDone()));
             if (!valid) p = qmake(0.f, 0.f, 0.f, 0.f);
             if (active) stq(poses_all + ((size_t)t * Nc + c) * 4, p);
             if (t == T - 1) break;
@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(kST)
             for (int k = 0; k < KMAX; ++k) {
                 b[k] *= st.a[k] * one_minus_dist(qdot(p, v[k]));
                 acc[10] += fabsf(b[k]);
+                acc[12] += b[k];
                 acc_rank1(acc, b[k], v[k]);
             }
         }

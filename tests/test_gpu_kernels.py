@@ -389,3 +389,21 @@ def test_routing_small(B, P, K, O, T):
         e = rel_err(p.grad.cpu(), ref[k + 2])
         print("small margin k=%d err=%.2e tol=%.2e" % (k, e, tol))
         assert e < tol, (k, e, tol)
+
+
+def test_routing_negative_activations():
+    """outside the reference's domain (activations are sigmoid outputs / masks) but inside the API's:
+    negative weights make M indefinite; the LARGEST eigenvalue must still be the one that is followed"""
+    from qecnetworks_b200 import functional as QF
+
+    dev = cuda()
+    gen = torch.Generator().manual_seed(123)
+    B, P, O, J, T = 2, 3, 5, 12, 2
+    votes = clustered((B, P, O, J), gen, spread=0.3)
+    act = torch.rand(B, P, J, generator=gen) * 0.6 + 0.3
+    act[:, :, 3::4] *= -0.5
+    alpha, beta = torch.tensor([1.0]), torch.tensor([1.0])
+    pose_ref, agr_ref = orc.routing(votes.double(), act.double(), alpha.double(), beta.double(), T)
+    pose, agr = QF.routing(votes.to(dev), act.to(dev), alpha.to(dev), beta.to(dev), T)
+    assert quat_err(pose.cpu(), pose_ref) < TOL
+    assert max_err(agr.cpu(), agr_ref) < TOL
