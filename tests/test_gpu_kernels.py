@@ -407,3 +407,28 @@ def test_routing_negative_activations():
     pose, agr = QF.routing(votes.to(dev), act.to(dev), alpha.to(dev), beta.to(dev), T)
     assert quat_err(pose.cpu(), pose_ref) < TOL
     assert max_err(agr.cpu(), agr_ref) < TOL
+
+
+def test_gather_golden_gpu():
+    """qec_gather against the outputs of the reference's own dataset class: bit-exact"""
+    from qecnetworks_b200 import functional as QF
+    from tests.util import load_golden as lg
+
+    dev = cuda()
+    g = lg("gather")
+    ps = torch.stack([g["s%d.point_set" % n] for n in range(3)]).to(dev)
+    ls = torch.stack([g["s%d.lrf_set" % n] for n in range(3)]).to(dev)
+    idx = torch.stack([g["s%d.idx" % n] for n in range(3)]).to(dev)
+    W = max(int(g["s%d.wrong_ids" % n].numel()) for n in range(3))
+    wrong = torch.full((3, W), -12345, dtype=torch.int64)
+    cnt = torch.zeros(3, dtype=torch.int32)
+    for n in range(3):
+        w = g["s%d.wrong_ids" % n]
+        wrong[n, : w.numel()] = w
+        cnt[n] = w.numel()
+    points, lrfs, act, err = QF.neighbour_gather(ps, ls, idx, wrong.to(dev), cnt.to(dev))
+    assert int(err.item()) == 0
+    for n in range(3):
+        assert torch.equal(points[n].cpu(), g["s%d.points" % n])
+        assert torch.equal(lrfs[n].cpu(), g["s%d.lrfs" % n])
+        assert torch.equal(act[n].cpu(), g["s%d.act" % n])

@@ -153,3 +153,25 @@ def test_full_size_properties():
         pose_r, a_r = net(points_r, lrfs_r, act, None)
     assert max_err(a_r.cpu(), a.detach().cpu()) < TOL
     assert quat_err(ham(q.expand_as(pose), pose.detach()).cpu(), pose_r.cpu()) < 5e-4
+
+
+@pytest.mark.parametrize("K,O,T", [(9, 32, 1), (16, 64, 10), (32, 48, 5), (64, 512, 2), (9, 512, 7)])
+def test_stress_sweep_corners(K, O, T):
+    """BASELINE config 5 geometry (P=64, I=1, K in 9..64, O in 32..512, T in 1..10) at a small batch,
+    inference only: the drop-in module against the oracle"""
+    import qecnetworks_b200 as qb
+
+    dev = cuda()
+    B, P = 2, 64
+    params = orc.init_module_params(1, O, seed=K + O)
+    params["quater_gen2.bias"] = params["quater_gen2.bias"] + torch.tensor([1.5, 0.2, -0.3, 0.4]).repeat_interleave(O)
+    points, lrfs, act, _ = orc.synthetic_batch(B, P=P, K=K, seed=K * 3 + T)
+    pose_ref, agr_ref = orc.qec_module_forward({k: v.double() for k, v in params.items()}, points.double(),
+                                               lrfs.unsqueeze(-2).double(), act.unsqueeze(-1).double(), T)
+    mod = qb.QecModule(1, O, num_iterations=T, num_neighbours=K, num_patches=P)
+    mod.load_state_dict(params)
+    mod = mod.to(dev)
+    with torch.no_grad():
+        pose, agr = mod(points.to(dev), lrfs.unsqueeze(-2).to(dev), act.unsqueeze(-1).to(dev))
+    assert quat_err(pose.cpu(), pose_ref) < TOL
+    assert max_err(agr.cpu(), agr_ref) < TOL

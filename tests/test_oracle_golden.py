@@ -136,3 +136,15 @@ def test_equivariance():
     p1, a1 = orc.qec_net_forward(params, points_r, lrfs_r, act, 3)
     assert max_err(a0, a1) < 1e-9
     assert quat_err(orc.ham(q.expand_as(p0), p0), p1) < 1e-9
+
+
+def test_gather_golden():
+    """the loader gather (SURVEY 8a row d) against outputs of the reference's own dataset class
+    (tests/golden/make_golden_gather.py): bit-exact"""
+    g = load_golden("gather")
+    for n in range(3):
+        p, l, a = orc.neighbour_gather(g["s%d.point_set" % n], g["s%d.lrf_set" % n], g["s%d.idx" % n],
+                                       g["s%d.wrong_ids" % n])
+        assert torch.equal(p, g["s%d.points" % n])
+        assert torch.equal(l, g["s%d.lrfs" % n])
+        assert torch.equal(a, g["s%d.act" % n])
