@@ -133,10 +133,28 @@ int qec_gather(const float* point_set, const float* lrf_set, const long long* id
                const int* wrong_count, float* points, float* lrfs, float* act, int* err, int B, int N, int P, int K,
                int Wmax, void* stream);
 
+/* The two generations behind qec_routing_fused_*: the packed-pair kernels (FFMA2, even I;
+ * routing_fused2.cu) are used whenever qec_routing_fused_packed_supported returns 1, otherwise
+ * the scalar kernels, which are also exported on their own so that tests can cross-check the
+ * two on the same inputs.  Same arguments and semantics as qec_routing_fused_fwd / _bwd. */
+int qec_routing_fused_packed_supported(int K, int I, int O, int T);
+int qec_routing_fused_fwd_scalar(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
+                                 const float* beta, float* pose, float* agreement, float* poses_all, float* stats,
+                                 int BP, int K, int I, int O, int T, void* stream);
+int qec_routing_fused_bwd_scalar(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
+                                 const float* beta, const float* poses_all, const float* stats, const float* g_pose,
+                                 const float* g_agreement, float* g_toqi, float* g_lrfs, float* g_act,
+                                 float* g_alpha_beta, int BP, int K, int I, int O, int T, void* stream);
+
 /* FP32 FMA roof: blocks*256 threads x iters x 16 dependent-chain FMAs
  * (2*16*iters*256*blocks FLOP); timed by the caller with CUDA events.  No reference
  * counterpart: it measures the denominator of the FP32 roofline on the box. */
 int qec_ffma_peak(float* out, int blocks, int iters, void* stream);
+
+/* Issue-slot / pipe-sharing probe for the packed FP32 instructions of sm_100 (FFMA2):
+ * mode 0: 16 FFMA | 1: 16 FFMA2 | 2: 8 FFMA + 8 FMNMX | 3: 8 FFMA2 + 8 FMNMX | 4: 8 FFMA2 + 8 FFMA |
+ * 5: 8 FFMA2 | 6: 8 FFMA | 7: 16 FMNMX chains per thread, iters rounds.  No reference counterpart. */
+int qec_pipe_probe(float* out, int blocks, int iters, int mode, void* stream);
 
 #ifdef __cplusplus
 }

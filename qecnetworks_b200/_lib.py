@@ -25,6 +25,9 @@ SIGNATURES = {
     "qec_routing_fused_supported": ([_I, _I, _I, _I], 0),
     "qec_routing_fused_fwd": ([_P] * 9 + [_I, _I, _I, _I, _I, _P], 1),
     "qec_routing_fused_bwd": ([_P] * 13 + [_I, _I, _I, _I, _I, _P], 1),
+    "qec_routing_fused_packed_supported": ([_I, _I, _I, _I], 0),
+    "qec_routing_fused_fwd_scalar": ([_P] * 9 + [_I, _I, _I, _I, _I, _P], 1),
+    "qec_routing_fused_bwd_scalar": ([_P] * 13 + [_I, _I, _I, _I, _I, _P], 1),
     "qec_routing_small_supported": ([_I, _I, _I, _I], 0),
     "qec_routing_small_fwd": ([_P] * 11 + [_I, _I, _I, _I, _P], 1),
     "qec_routing_small_bwd": ([_P] * 14 + [_I, _I, _I, _I, _P], 1),
@@ -32,6 +35,7 @@ SIGNATURES = {
     "qec_symeig4_bwd": ([_P, _P, _P, _P, _P, _LL, _I, _P], 1),
     "qec_gather": ([_P] * 9 + [_I, _I, _I, _I, _I, _P], 1),
     "qec_ffma_peak": ([_P, _I, _I, _P], 1),
+    "qec_pipe_probe": ([_P, _I, _I, _I, _P], 1),
 }
 
 _lib = None

@@ -1,0 +1,542 @@
+// routing_fused2.cu -- the cluster-resident routing kernels of the pool2 regime, second
+// generation: PACKED vote pairs (FFMA2) and asynchronous prefetch of the next capsule.
+//
+// Same contract as routing_fused.cu (reference models/qec_module.py:126-147, 172-194): vote
+// generation + all T routing iterations + the activation epilogue of one output capsule with
+// its votes resident in the shared memory of a thread-block cluster; the [B,P,O,K*I,4] vote
+// tensor never exists in HBM.  What changed, and why (profiles/r01_fused_v5*: the first
+// generation is bound by instruction issue -- issue slots 46 % busy, fma pipe 27 %, DRAM 12 %,
+// top stall = barrier):
+//
+//  * Votes are processed as PAIRS (j, j+1) = inputs (k, i), (k, i+1) held in the low / high half
+//    of 64-bit register pairs and every FP32 operation of a sweep is one FFMA2 / FMUL2 /
+//    FADD2 for both (f32x2.cuh).  A routing sweep costs ~21 issue slots per vote instead of
+//    ~40.  Shared memory keeps the pair component-interleaved, {w0 w1 x0 x1} {y0 y1 z0 z1},
+//    so a pair is two conflict-free LDS.128 straight into aligned register pairs; the
+//    transforms arrive the same way with LDG.64 / 8-byte cp.async because i is the
+//    contiguous axis of the capsule-major transform layout t_oqi.
+//  * The transforms of the NEXT capsule are copied global -> shared with cp.async directly
+//    into the vote slots while the epilogue sweep of the current capsule frees them, one
+//    commit group per slot, so HBM latency hides behind the epilogue sweep and the first
+//    reduction instead of stalling sweep 0.
+//  * The epilogue's two sums ride in the next capsule's first reduction (15 of the 16 lanes
+//    of the reducer), so a capsule costs T cluster reductions instead of T + 1.
+//
+// Requires I even (pairs never straddle a neighbour row and stay 8-byte aligned); other
+// geometries use the scalar kernels of routing_fused.cu.
+#include <cooperative_groups.h>
+
+#include "f32x2.cuh"
+#include "routing_core.cuh"
+#include "routing_fused_shared.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace qec {
+
+constexpr int kPT = 256;         // threads per CTA
+constexpr int kPairs = 8;        // resident vote pairs per thread
+constexpr int kNpMax = kPT * kPairs;  // 2048 pairs = 4096 votes per CTA
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ Quat2 lds_pair(const float4* sA, const float4* sB, int ps) {
+    const float4 a = sA[ps], b = sB[ps];
+    Quat2 v;
+    v.w = pk(a.x, a.y); v.x = pk(a.z, a.w); v.y = pk(b.x, b.y); v.z = pk(b.z, b.w);
+    return v;
+}
+__device__ __forceinline__ void sts_pair(float4* sA, float4* sB, int ps, const Quat2& v) {
+    sA[ps] = make_float4(lo(v.w), hi(v.w), lo(v.x), hi(v.x));
+    sB[ps] = make_float4(lo(v.y), hi(v.y), lo(v.z), hi(v.z));
+}
+__device__ __forceinline__ f2 lds_f2(const float2* p) {
+    const float2 v = *p;
+    return pk(v.x, v.y);
+}
+__device__ __forceinline__ void sts_f2(float2* p, f2 v) { *p = make_float2(lo(v), hi(v)); }
+__device__ __forceinline__ f2 ldg_f2(const float* p) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+    return pk(v.x, v.y);
+}
+
+
+// ------------------------------------------------------------------------------------
+// Cluster-wide sum of <= 16 floats per thread without a cluster barrier.
+//   1. every thread parks its N partials in shared memory, one CTA barrier;
+//   2. 16 lanes per value add 16 entries each and finish with a 4-step butterfly;
+//   3. the 16 group leaders PUSH the CTA's N sums into the receive buffer of every CTA of the
+//      cluster with st.async (remote shared-memory store that signals the destination's
+//      mbarrier with its byte count);
+//   4. warp 0 of every CTA waits on its own mbarrier and adds the CL partials in a fixed order,
+//      so all CTAs continue with bit-identical totals and nothing has to be broadcast between
+//      CTAs.  Receive buffers are double-buffered by phase; the pose broadcast inside the CTA
+//      (bcast) is the second and last CTA barrier of a sweep.
+// Compared with barrier.cluster + DSMEM loads (ClusterReducer) this removes the cluster-scope
+// MEMBAR, one DSMEM round trip and two CTA barriers from the serial path of every sweep.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_f32(unsigned remote_addr, float v, unsigned remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+                 "r"(__float_as_uint(v)), "r"(remote_mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int CL>
+struct PushReducer {
+    static constexpr int NT = kPT;
+    static constexpr int kRows = 15;  // widest accumulator; 2 CTAs/SM leave room for no more
+    static constexpr int kSmemFloats = kRows * NT + 2 * CL * 16 + 16 + 4;
+    float* scr;   // [kRows][NT] per-thread partials
+    float* buf;   // [2][CL][16] received CTA sums
+    float* out;   // [16] solve result
+    unsigned mbar, rank, phase;
+    __device__ __forceinline__ PushReducer(float* s, unsigned rank_)
+        : scr(s), buf(s + kRows * NT), out(s + kRows * NT + 2 * CL * 16), rank(rank_), phase(0) {
+        mbar = smem_u32(out + 16);  // two mbarriers (8 bytes each), one per receive buffer
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar + 8) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        cluster_sync_all();  // every CTA of the cluster is resident and its mbarrier initialised
+    }
+    template <int N>
+    __device__ __forceinline__ void reduce(float (&a)[N]) {
+        static_assert(N <= kRows, "accumulator too wide");
+        const int tid = threadIdx.x;
+        // phase n uses receive buffer / mbarrier n & 1.  A peer can be at most one phase ahead, so a
+        // push of phase n + 1 never lands in the mbarrier that still collects phase n.
+        const unsigned mb = mbar + 8u * (phase & 1u);
+#pragma unroll
+        for (int i = 0; i < N; ++i) scr[i * NT + tid] = a[i];
+        if (tid == 0)  // arm this phase: N floats from each of the CL CTAs
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(N * CL * 4) : "memory");
+        __syncthreads();
+        const int v = tid >> 4, part = tid & 15;
+        float s = 0.f;
+        if (v < N) {
+            const float4* row = reinterpret_cast<const float4*>(scr + v * NT + part * 16);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // rotated start: conflict-free LDS.128
+                const float4 q = row[((part >> 1) + k) & 3];
+                s += (q.x + q.y) + (q.z + q.w);
+            }
+        }
+#pragma unroll
+        for (int d = 8; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (v < N && part == 0) {
+            const unsigned slot = smem_u32(buf + ((phase & 1u) * CL + rank) * 16 + v);
+#pragma unroll
+            for (int r = 0; r < CL; ++r) st_async_f32(mapa_u32(slot, r), s, mapa_u32(mb, r));
+        }
+        if (tid < 32) {
+            const unsigned parity = (phase >> 1) & 1u;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "WAIT_%=:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                "@!p bra WAIT_%=;\n\t}" ::"r"(mb), "r"(parity)
+                : "memory");
+            float t = 0.f;
+            if (tid < 16) {
+                const float* b = buf + (phase & 1u) * CL * 16 + tid;
+#pragma unroll
+                for (int r = 0; r < CL; ++r) t += b[r * 16];  // fixed order: identical bits in every CTA
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) a[i] = __shfl_sync(0xffffffffu, t, i);
+        }
+        ++phase;
+    }
+    __device__ __forceinline__ bool solver() const { return threadIdx.x < 32; }
+    template <int N>
+    __device__ __forceinline__ void bcast(float (&r)[N]) {
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) out[i] = r[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < N; ++i) r[i] = out[i];
+    }
+    // a reduction whose result only warp 0 consumes still needs the CTA to stay behind the solver
+    // before scr is reused: callers follow it with bcast() or sync()
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+
+// two votes at once (reference models/qec_module.py:129-145, scalar twin: make_vote in vote_math.cuh)
+struct VotePair {
+    Quat2 vote;
+    Quat2 that;  // normalised transform before the hemisphere fix
+    Quat2 t;     // fix(that)
+    f2 rn, st, sv;
+};
+// sign(x) with sign(0) = 0 as clamp(x * 2^126, -1, 1): exact for every normal x (denormals are
+// flushed to zero by -ftz, like in the comparisons of fsign); 1 FMUL2 + 4 FMNMX per pair
+__device__ __forceinline__ f2 sign2(f2 x) {
+    const f2 y = mul2(x, bc(8.507059173e37f));
+    return pk(fminf(fmaxf(lo(y), -1.f), 1.f), fminf(fmaxf(hi(y), -1.f), 1.f));
+}
+__device__ __forceinline__ float rnorm_eps(float n2) { return (n2 > 1e-24f) ? frsqrt(n2) : 1e12f; }
+
+template <bool kKeepParts>
+__device__ __forceinline__ VotePair make_vote2(const Quat2& lrf, const Quat2& traw) {
+    VotePair r;
+    const f2 n2 = qdot2(traw, traw);
+    r.rn = pk(rnorm_eps(lo(n2)), rnorm_eps(hi(n2)));  // x / max(|x|, eps)
+    const f2 thw = mul2(traw.w, r.rn);
+    if (kKeepParts) {
+        r.st = sign2(thw);
+        r.that = qscale2(traw, r.rn);
+        r.t = qscale2(r.that, r.st);
+        const Quat2 h = qham2(lrf, r.t);
+        r.sv = sign2(h.w);
+        r.vote = qscale2(h, r.sv);
+    } else {
+        // fix(l (x) fix(that)) == fix(l (x) that) unless that.w == 0 (then the vote is zeroed): a sign
+        // flip of t flips the product exactly and the outer hemisphere fix absorbs it
+        r.that.w = thw; r.that.x = mul2(traw.x, r.rn); r.that.y = mul2(traw.y, r.rn); r.that.z = mul2(traw.z, r.rn);
+        const Quat2 h = qham2(lrf, r.that);
+        const f2 s = sign2(h.w);
+        r.sv = pk((lo(thw) != 0.f) ? lo(s) : 0.f, (hi(thw) != 0.f) ? hi(s) : 0.f);
+        r.vote = qscale2(h, r.sv);
+    }
+    return r;
+}
+
+
+// ------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------
+struct PairGeom {
+    int np;              // pairs of this CTA
+    int off[kPairs];     // k * trow + i of the pair's first vote (element offset inside the bp block of t_oqi)
+    int I;
+};
+
+// issue the asynchronous copy of capsule (bp, o)'s transforms into the vote slots, one commit group per slot
+template <bool FULL>
+__device__ __forceinline__ void prefetch_slot(const PairGeom& G, const float* tcap, float4* sA, float4* sB, int m) {
+    const int ps = threadIdx.x + m * kPT;
+    if (FULL || ps < G.np) {
+        const float* tp = tcap + G.off[m];
+        float* a = reinterpret_cast<float*>(sA + ps);
+        float* b = reinterpret_cast<float*>(sB + ps);
+        cp_async8(a, tp);
+        cp_async8(a + 2, tp + G.I);
+        cp_async8(b, tp + 2 * G.I);
+        cp_async8(b + 2, tp + 3 * G.I);
+    }
+    cp_async_commit();
+}
+
+template <int M>
+__device__ __forceinline__ void wait_slot() {  // slot M's group is complete (groups are committed in slot order)
+    cp_async_wait<kPairs - 1 - M>();
+}
+
+// FULL: every thread owns exactly kPairs resident pairs (J == CL * 4096, e.g. pool2 of QEC-Net):
+// no per-slot guards, so the unrolled sweeps are straight-line code the scheduler can interleave.
+template <int CL, bool FULL>
+__global__ void __launch_bounds__(kPT, 2)
+    routing_fused2_fwd_kernel(const float* __restrict__ t_oqi, const float* __restrict__ lrfs,
+                              const float* __restrict__ act, const float* __restrict__ alpha_p,
+                              const float* __restrict__ beta_p, float* __restrict__ pose,
+                              float* __restrict__ agreement, float* __restrict__ poses_all,
+                              float* __restrict__ stats, long long Nc, int K, int I, int O, int T) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* __restrict__ sA = reinterpret_cast<float4*>(smem_raw);   // {w0 w1 x0 x1} per pair
+    float4* __restrict__ sB = sA + kNpMax;                           // {y0 y1 z0 z1}
+    float2* __restrict__ sa = reinterpret_cast<float2*>(sB + kNpMax);  // activations of the pair
+    float2* __restrict__ sb = sa + kNpMax;                           // routing weights b^t of the pair
+    unsigned rank;
+    asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    PushReducer<CL> red(reinterpret_cast<float*>(sb + kNpMax), rank);
+    const long long cid = blockIdx.x / CL, ncl = gridDim.x / CL;
+    const int J = K * I;
+    const int Jc = 2 * ((J / 2 + CL - 1) / CL);  // even slice per CTA
+    const int j_begin = min(J, (int)rank * Jc);
+    const int nloc = min(J, j_begin + Jc) - j_begin;
+    const float alpha = __ldg(alpha_p), beta = __ldg(beta_p);
+    const size_t trow = (size_t)4 * I * O;
+    const bool writer = (rank == 0) && (threadIdx.x == 0);
+
+    PairGeom G;
+    G.np = nloc / 2;
+    G.I = I;
+#pragma unroll
+    for (int m = 0; m < kPairs; ++m) {
+        const int j = j_begin + 2 * (threadIdx.x + m * kPT);
+        const int k = j / I;
+        G.off[m] = (int)(k * trow) + (j - k * I);
+    }
+    auto tcap_of = [&](long long c) {
+        const long long bp = c / O;
+        const int o = (int)(c - bp * O);
+        return t_oqi + (size_t)bp * K * trow + (size_t)o * 4 * I;
+    };
+    auto live = [&](int m) { return FULL || (threadIdx.x + m * kPT < G.np); };
+
+    if (cid < Nc) {
+        const float* tc = tcap_of(cid);
+#pragma unroll
+        for (int m = 0; m < kPairs; ++m) prefetch_slot<FULL>(G, tc, sA, sB, m);
+    }
+    bool pend = false;       // the previous capsule's epilogue sums wait for this capsule's first reduction
+    long long pend_c = 0;
+    float e0 = 0.f, e1 = 0.f;
+    Quat p = qmake(0.f, 0.f, 0.f, 0.f);
+
+    auto finish = [&](long long c, Quat pf, float es, float en) {  // reference qec_module.py:188-193
+        const float s = (en > 0.f) ? es / en : 0.f;
+        stq(pose + (size_t)c * 4, pf);
+        agreement[c] = (en > 0.f) ? sigmoidf(fmaf(alpha, s, beta - 1.f)) : 0.f;
+        stats[2 * c] = s;
+        stats[2 * c + 1] = en;
+    };
+
+    for (long long c = cid; c < Nc; c += ncl) {
+        const long long bp = c / O;
+        const float* lrf_c = lrfs + ((size_t)bp * J + j_begin) * 4;
+        const float* act_c = act + (size_t)bp * J + j_begin;
+        // ---- sweep 0: votes from the prefetched transforms, M^0 = sum a v v^T, b^0 = a ----------
+        float acc[15];
+        {
+            f2 m2[10], ssum = bc(0.f), comp = bc(0.f);
+            float sabs = 0.f;
+#pragma unroll
+            for (int i = 0; i < 10; ++i) m2[i] = bc(0.f);
+            auto gen = [&](int m, const Quat2& lrf, f2 a) {
+                const int ps = threadIdx.x + m * kPT;
+                const Quat2 traw = lds_pair(sA, sB, ps);
+                const Quat2 v = make_vote2<false>(lrf, traw).vote;
+                sts_pair(sA, sB, ps, v);
+                sts_f2(sa + ps, a);
+                sts_f2(sb + ps, a);
+                sabs = (sabs + fabsf(lo(a))) + fabsf(hi(a));
+                ssum = add2(ssum, a);
+                acc_rank1_2(m2, a, v);
+                comp = add2(comp, add2(add2(v.w, v.x), add2(v.y, v.z)));
+            };
+            auto ldl = [&](int m, Quat2& lrf, f2& a) {  // the pair's LRFs and activations (L2-resident: shared by all O)
+                const int ps = threadIdx.x + m * kPT;
+                if (live(m)) {
+                    const Quat l0 = ldq_nc(lrf_c + (size_t)ps * 8), l1 = ldq_nc(lrf_c + (size_t)ps * 8 + 4);
+                    lrf = pk(l0, l1);
+                    a = ldg_f2(act_c + 2 * ps);
+                }
+            };
+            Quat2 lr[3];  // loads run two slots ahead of their use
+            f2 av[3];
+            ldl(0, lr[0], av[0]);
+            ldl(1, lr[1], av[1]);
+#define QEC_GEN_SLOT(M)                                                       \
+    if ((M) + 2 < kPairs) ldl((M) + 2, lr[((M) + 2) % 3], av[((M) + 2) % 3]); \
+    wait_slot<(M)>();                                                         \
+    if (live(M)) gen((M), lr[(M) % 3], av[(M) % 3]);
+            QEC_GEN_SLOT(0) QEC_GEN_SLOT(1) QEC_GEN_SLOT(2) QEC_GEN_SLOT(3)
+            QEC_GEN_SLOT(4) QEC_GEN_SLOT(5) QEC_GEN_SLOT(6) QEC_GEN_SLOT(7)
+#undef QEC_GEN_SLOT
+#pragma unroll
+            for (int i = 0; i < 10; ++i) acc[i] = hsum(m2[i]);
+            acc[10] = sabs;
+            acc[11] = hsum(ssum);
+            acc[12] = hsum(comp);
+            acc[13] = e0;
+            acc[14] = e1;
+        }
+        red.reduce(acc);
+        bool valid = false;
+        float r[4] = {0.f, 0.f, 0.f, 0.f};
+        if (red.solver()) {
+            if (pend && writer) finish(pend_c, p, acc[13], acc[14]);
+            valid = acc[12] != 0.f;  // reference qec_module.py:72-73
+            const Quat q = solve_pose(acc, valid);
+            r[0] = q.w; r[1] = q.x; r[2] = q.y; r[3] = q.z;
+        }
+        red.bcast(r);
+        p = qmake(r[0], r[1], r[2], r[3]);
+        if (writer) stq(poses_all + (size_t)c * 4, p);
+        // ---- sweeps 1..T-1: b <- b a (1 - d(pose, v)), M^t = sum b v v^T, all from shared memory
+        for (int t = 1; t < T; ++t) {
+            f2 m2[10], ssum = bc(0.f);
+            float sabs = 0.f;
+#pragma unroll
+            for (int i = 0; i < 10; ++i) m2[i] = bc(0.f);
+#pragma unroll
+            for (int m = 0; m < kPairs; ++m) {
+                const int ps = threadIdx.x + m * kPT;
+                if (live(m)) {
+                    const Quat2 v = lds_pair(sA, sB, ps);
+                    const f2 a = lds_f2(sa + ps), b0 = lds_f2(sb + ps);
+                    const f2 b = mul2(b0, mul2(a, one_minus_dist2(qdot2(p, v))));
+                    sts_f2(sb + ps, b);
+                    sabs = (sabs + fabsf(lo(b))) + fabsf(hi(b));
+                    ssum = add2(ssum, b);
+                    acc_rank1_2(m2, b, v);
+                }
+            }
+            float a2[12];
+#pragma unroll
+            for (int i = 0; i < 10; ++i) a2[i] = hsum(m2[i]);
+            a2[10] = sabs;
+            a2[11] = hsum(ssum);
+            red.reduce(a2);
+            if (red.solver()) {
+                const Quat q = solve_pose(a2, valid);
+                r[0] = q.w; r[1] = q.x; r[2] = q.y; r[3] = q.z;
+            }
+            red.bcast(r);
+            p = qmake(r[0], r[1], r[2], r[3]);
+            if (writer) stq(poses_all + ((size_t)t * Nc + c) * 4, p);
+        }
+        // ---- epilogue sweep (reference qec_module.py:188-193); each slot is refilled with the next
+        // capsule's transforms as soon as its vote has been read
+        {
+            const long long cn = c + ncl;
+            const bool more = cn < Nc;
+            const float* tn = more ? tcap_of(cn) : t_oqi;
+            f2 es = bc(0.f);
+            float en = 0.f;
+#pragma unroll
+            for (int m = 0; m < kPairs; ++m) {
+                const int ps = threadIdx.x + m * kPT;
+                if (live(m)) {
+                    const Quat2 v = lds_pair(sA, sB, ps);
+                    const f2 b = lds_f2(sb + ps);
+                    es = fma2(b, one_minus_dist2(qdot2(p, v)), es);
+                    en += ((lo(b) != 0.f) ? 1.f : 0.f) + ((hi(b) != 0.f) ? 1.f : 0.f);
+                }
+                if (more) prefetch_slot<FULL>(G, tn, sA, sB, m);
+            }
+            e0 = hsum(es);
+            e1 = en;
+            pend = true;
+            pend_c = c;
+        }
+    }
+    if (pend) {
+        float e[2] = {e0, e1};
+        red.reduce(e);
+        if (red.solver() && writer) finish(pend_c, p, e[0], e[1]);
+    }
+    cluster_sync_all();  // no CTA may exit while a peer can still push into its receive buffers
+}
+
+template <int CL>
+constexpr size_t fwd2_smem() {
+    return (2 * sizeof(float4) + 2 * sizeof(float2)) * kNpMax + sizeof(float) * PushReducer<CL>::kSmemFloats;
+}
+
+// like fused_grid (routing_fused_shared.cuh) but the cluster attribute is set for CL = 1 too: the
+// push reducer addresses its own CTA through the cluster window as well
+template <class Kern>
+static int fused2_grid(Kern kern, int CL, size_t smem, long long Nc, cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr,
+                       int& cached_clusters) {
+    cfg.blockDim = dim3(kPT);
+    cfg.dynamicSmemBytes = smem;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.numAttrs = 1;
+    cfg.attrs = attr;
+    int clusters = cached_clusters;
+    if (clusters < 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        cfg.gridDim = dim3(CL * 4 * kNumSMs);  // upper bound for the occupancy query
+        e = cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg);
+        if (e != cudaSuccess) return (int)e;
+        if (clusters < 1) return (int)cudaErrorLaunchOutOfResources;
+        cached_clusters = clusters;
+    }
+    if (clusters > Nc) clusters = (int)Nc;
+    cfg.gridDim = dim3((unsigned)(clusters * CL));
+    return 0;
+}
+
+template <int CL>
+static int launch_fused2_fwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
+                             const float* beta, float* pose, float* agreement, float* poses_all, float* stats,
+                             long long Nc, int K, int I, int O, int T, cudaStream_t st) {
+    const bool full = ((long long)K * I == (long long)CL * 2 * kNpMax);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    static int cached[2] = {-1, -1};
+    cudaError_t e;
+    if (full) {
+        auto kern = routing_fused2_fwd_kernel<CL, true>;
+        const int rc = fused2_grid(kern, CL, fwd2_smem<CL>(), Nc, cfg, attr, cached[1]);
+        if (rc) return rc;
+        cfg.stream = st;
+        e = cudaLaunchKernelEx(&cfg, kern, t_oqi, lrfs, act, alpha, beta, pose, agreement, poses_all, stats, Nc, K, I,
+                               O, T);
+    } else {
+        auto kern = routing_fused2_fwd_kernel<CL, false>;
+        const int rc = fused2_grid(kern, CL, fwd2_smem<CL>(), Nc, cfg, attr, cached[0]);
+        if (rc) return rc;
+        cfg.stream = st;
+        e = cudaLaunchKernelEx(&cfg, kern, t_oqi, lrfs, act, alpha, beta, pose, agreement, poses_all, stats, Nc, K, I,
+                               O, T);
+    }
+    return e == cudaSuccess ? launch_status() : (int)e;
+}
+
+}  // namespace qec
+
+using namespace qec;
+
+// 1 if the packed-pair kernels serve this geometry (callers normally just call qec_routing_fused_*,
+// which dispatch here when possible)
+extern "C" int qec_routing_fused_packed_supported(int K, int I, int O, int T) {
+    if (K <= 0 || I <= 0 || O <= 0 || (I & 1)) return 0;
+    const long long J = (long long)K * I;
+    if (J > 8ll * kJcMax) return 0;
+    if (4ll * J * O >= (1ll << 31)) return 0;  // 32-bit element offsets inside one bp block of t_oqi
+    return (T >= 1 && T <= kTB && pick_cluster((int)J) > 0) ? 1 : 0;
+}
+
+extern "C" int qec_routing_fused_fwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
+                                     const float* beta, float* pose, float* agreement, float* poses_all,
+                                     float* stats, int BP, int K, int I, int O, int T, void* stream) {
+    if (!qec_routing_fused_packed_supported(K, I, O, T))
+        return qec_routing_fused_fwd_scalar(t_oqi, lrfs, act, alpha, beta, pose, agreement, poses_all, stats, BP, K, I,
+                                            O, T, stream);
+    QEC_CHECK_ARG(t_oqi, 1);
+    QEC_CHECK_ARG(lrfs, 2);
+    QEC_CHECK_ARG(act && alpha && beta, 3);
+    QEC_CHECK_ARG(pose && agreement && poses_all && stats, 6);
+    QEC_CHECK_ARG(BP > 0, 10);
+    const int CL = pick_cluster(K * I);
+    const long long Nc = (long long)BP * O;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    QEC_DISPATCH_CL(launch_fused2_fwd, t_oqi, lrfs, act, alpha, beta, pose, agreement, poses_all, stats, Nc, K, I, O,
+                    T, st)
+}
+
+extern "C" int qec_routing_fused_bwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
+                                     const float* beta, const float* poses_all, const float* stats,
+                                     const float* g_pose, const float* g_agreement, float* g_toqi, float* g_lrfs,
+                                     float* g_act, float* g_alpha_beta, int BP, int K, int I, int O, int T,
+                                     void* stream) {
+    return qec_routing_fused_bwd_scalar(t_oqi, lrfs, act, alpha, beta, poses_all, stats, g_pose, g_agreement, g_toqi,
+                                        g_lrfs, g_act, g_alpha_beta, BP, K, I, O, T, stream);
+}

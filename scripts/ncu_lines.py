@@ -2,6 +2,7 @@
 import csv, subprocess, sys
 rep, kern = sys.argv[1], sys.argv[2]
 topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+by = 1 if (len(sys.argv) > 4 and sys.argv[4] == "samples") else 0
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "-k", "regex:" + kern],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
@@ -20,5 +21,5 @@ for r in rows:
         lines[key] = (inst, samp, r[1].strip()[:90])
 tot = sum(v[0] for v in lines.values()); tots = sum(v[1] for v in lines.values())
 print("total warp-instructions", tot, "samples", tots)
-for (f, ln), (inst, samp, src) in sorted(lines.items(), key=lambda kv: -kv[1][0])[:topn]:
+for (f, ln), (inst, samp, src) in sorted(lines.items(), key=lambda kv: -kv[1][by])[:topn]:
     print(f"{100*inst/tot:5.1f}% inst {100*samp/max(tots,1):5.1f}% smp  {f}:{ln:<4d} {src}")
