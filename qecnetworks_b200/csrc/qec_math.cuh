@@ -358,6 +358,91 @@ QEC_HD Quat top_eigvec_psd(const Sym4& m0, AllDone all_done) {
     return (zero || !(n2 > 0.f)) ? qmake(0.f, 0.f, 0.f, 1.f) : qscale(v, frsqrt(n2));
 }
 
+// 2^-floor(log2 x) for a normal positive x (x * result lies in [1, 2)): an exact power-of-two
+// rescale costs one integer subtract instead of a reciprocal
+QEC_HD float pow2_rescale(float x) {
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(0x7f000000 - (__float_as_int(x) & 0x7f800000));
+#else
+    int e;
+    frexpf(x, &e);
+    return ldexpf(1.f, 1 - e);
+#endif
+}
+
+// Same iteration as top_eigvec_psd with the serial latency cut for the kernels where one warp
+// solves while a whole cluster waits (routing_fused2.cu): two squarings per round, rescaled by an
+// exact power of two (no reciprocal; between rescales the top eigenvalue stays within
+// [2^-8, 2^4]), one convergence test per round on the scale-free ratio
+//   sum_i lambda_i^2 >= (1 - 1e-5) (sum_i lambda_i)^2   of the once-squared matrix B;
+// the vector is extracted from B^2, whose second-to-first eigenvalue ratio is then below 3e-11.
+#define QEC_POWER2_MAX_ROUNDS 13
+
+// Gershgorin lower bound of the smallest eigenvalue, clamped at 0.  Subtracting it from the
+// diagonal of a PSD matrix keeps it PSD (the top eigenvector stays the dominant one) and turns
+// the ratio lambda_2/lambda_1 into (lambda_2 - s)/(lambda_1 - s): when the spectrum is clustered --
+// votes spread all over the sphere, the slow case of the squaring iteration -- the matrix is
+// close to a multiple of the identity, the bound is tight and several squarings are saved.
+QEC_HD float gershgorin_shift(float a00, float a01, float a02, float a03, float a11, float a12, float a13, float a22,
+                              float a23, float a33) {
+    const float x01 = fabsf(a01), x02 = fabsf(a02), x03 = fabsf(a03), x12 = fabsf(a12), x13 = fabsf(a13),
+                x23 = fabsf(a23);
+    const float g0 = a00 - ((x01 + x02) + x03), g1 = a11 - ((x01 + x12) + x13), g2 = a22 - ((x02 + x12) + x23),
+                g3 = a33 - ((x03 + x13) + x23);
+    return fmaxf(fminf(fminf(g0, g1), fminf(g2, g3)), 0.f);
+}
+
+template <typename AllDone>
+QEC_HD Quat top_eigvec_psd2(const Sym4& m0, AllDone all_done) {
+    const float tr = m0.a00 + m0.a11 + m0.a22 + m0.a33;
+    const bool zero = !(tr > 0.f);
+    float s = zero ? 0.f : pow2_rescale(tr);
+    float a00 = m0.a00 * s, a01 = m0.a01 * s, a02 = m0.a02 * s, a03 = m0.a03 * s, a11 = m0.a11 * s,
+          a12 = m0.a12 * s, a13 = m0.a13 * s, a22 = m0.a22 * s, a23 = m0.a23 * s, a33 = m0.a33 * s;
+    for (int k = 0; k < QEC_POWER2_MAX_ROUNDS; ++k) {
+        {
+            const float sh = gershgorin_shift(a00, a01, a02, a03, a11, a12, a13, a22, a23, a33);
+            a00 -= sh; a11 -= sh; a22 -= sh; a33 -= sh;
+        }
+        // B = A^2
+        const float b00 = fmaf(a00, a00, fmaf(a01, a01, fmaf(a02, a02, a03 * a03)));
+        const float b01 = fmaf(a00, a01, fmaf(a01, a11, fmaf(a02, a12, a03 * a13)));
+        const float b02 = fmaf(a00, a02, fmaf(a01, a12, fmaf(a02, a22, a03 * a23)));
+        const float b03 = fmaf(a00, a03, fmaf(a01, a13, fmaf(a02, a23, a03 * a33)));
+        const float b11 = fmaf(a01, a01, fmaf(a11, a11, fmaf(a12, a12, a13 * a13)));
+        const float b12 = fmaf(a01, a02, fmaf(a11, a12, fmaf(a12, a22, a13 * a23)));
+        const float b13 = fmaf(a01, a03, fmaf(a11, a13, fmaf(a12, a23, a13 * a33)));
+        const float b22 = fmaf(a02, a02, fmaf(a12, a12, fmaf(a22, a22, a23 * a23)));
+        const float b23 = fmaf(a02, a03, fmaf(a12, a13, fmaf(a22, a23, a23 * a33)));
+        const float b33 = fmaf(a03, a03, fmaf(a13, a13, fmaf(a23, a23, a33 * a33)));
+        const float t2 = (b00 + b11) + (b22 + b33);
+        // C = B^2
+        const float c00 = fmaf(b00, b00, fmaf(b01, b01, fmaf(b02, b02, b03 * b03)));
+        const float c01 = fmaf(b00, b01, fmaf(b01, b11, fmaf(b02, b12, b03 * b13)));
+        const float c02 = fmaf(b00, b02, fmaf(b01, b12, fmaf(b02, b22, b03 * b23)));
+        const float c03 = fmaf(b00, b03, fmaf(b01, b13, fmaf(b02, b23, b03 * b33)));
+        const float c11 = fmaf(b01, b01, fmaf(b11, b11, fmaf(b12, b12, b13 * b13)));
+        const float c12 = fmaf(b01, b02, fmaf(b11, b12, fmaf(b12, b22, b13 * b23)));
+        const float c13 = fmaf(b01, b03, fmaf(b11, b13, fmaf(b12, b23, b13 * b33)));
+        const float c22 = fmaf(b02, b02, fmaf(b12, b12, fmaf(b22, b22, b23 * b23)));
+        const float c23 = fmaf(b02, b03, fmaf(b12, b13, fmaf(b22, b23, b23 * b33)));
+        const float c33 = fmaf(b03, b03, fmaf(b13, b13, fmaf(b23, b23, b33 * b33)));
+        const float t4 = (c00 + c11) + (c22 + c33);  // = sum lambda_B^2
+        const bool done = zero || (fmaf(-0.99999f * t2, t2, t4) >= 0.f);
+        const float r = zero ? 0.f : pow2_rescale(t4);
+        a00 = c00 * r; a01 = c01 * r; a02 = c02 * r; a03 = c03 * r; a11 = c11 * r;
+        a12 = c12 * r; a13 = c13 * r; a22 = c22 * r; a23 = c23 * r; a33 = c33 * r;
+        if (all_done(done)) break;
+    }
+    Quat v = qmake(a00, a01, a02, a03);
+    float best = a00;
+    if (a11 > best) { best = a11; v = qmake(a01, a11, a12, a13); }
+    if (a22 > best) { best = a22; v = qmake(a02, a12, a22, a23); }
+    if (a33 > best) { best = a33; v = qmake(a03, a13, a23, a33); }
+    const float n2 = qdot(v, v);
+    return (zero || !(n2 > 0.f)) ? qmake(0.f, 0.f, 0.f, 1.f) : qscale(v, frsqrt(n2));
+}
+
 // Top eigenvector of M = sum_j w_j v_j v_j^T / sum_j |w_j|  (so every eigenvalue lies in [-1, 1]).
 // Non-negative routing weights -- the reference's domain: 0/1 masks and sigmoid outputs -- make M
 // positive semi-definite and the squaring iteration applies directly.  If a weight was negative
@@ -368,6 +453,12 @@ QEC_HD Quat top_eigvec_weighted(Sym4 m, bool negative, AllDone all_done) {
     const float sh = negative ? 1.f : 0.f;
     m.a00 += sh; m.a11 += sh; m.a22 += sh; m.a33 += sh;
     return top_eigvec_psd(m, all_done);
+}
+template <typename AllDone>
+QEC_HD Quat top_eigvec_weighted2(Sym4 m, bool negative, AllDone all_done) {
+    const float sh = negative ? 1.f : 0.f;
+    m.a00 += sh; m.a11 += sh; m.a22 += sh; m.a33 += sh;
+    return top_eigvec_psd2(m, all_done);
 }
 
 // ---------------------------------------------------------------------------

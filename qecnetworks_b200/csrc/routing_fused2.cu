@@ -34,6 +34,24 @@ namespace cg = cooperative_groups;
 
 namespace qec {
 
+// Optional timeline instrumentation (build with QEC_NVCC_EXTRA=-DQEC_PROF; scripts/timeline_fused.py):
+// thread 0 of a few CTAs stamps clock64() at the phase boundaries of its first capsules.
+#ifdef QEC_PROF
+__device__ long long g_prof[8 * 64 * 32];
+#define QEC_EVT(id)                                                                                   \
+    do {                                                                                              \
+        if (threadIdx.x == 0 && blockIdx.x < 8 && prof_n < 64) g_prof[(blockIdx.x * 64 + prof_n) * 32 + (id)] = clock64(); \
+    } while (0)
+#define QEC_EVT_NEXT() (++prof_n)
+#else
+#define QEC_EVT(id) \
+    do {            \
+    } while (0)
+#define QEC_EVT_NEXT() \
+    do {               \
+    } while (0)
+#endif
+
 constexpr int kPT = 256;         // threads per CTA
 constexpr int kPairs = 8;        // resident vote pairs per thread
 constexpr int kNpMax = kPT * kPairs;  // 2048 pairs = 4096 votes per CTA
@@ -73,7 +91,7 @@ __device__ __forceinline__ f2 ldg_f2(const float* p) {
 // Cluster-wide sum of <= 16 floats per thread without a cluster barrier.
 //   1. every thread parks its N partials in shared memory, one CTA barrier;
 //   2. 16 lanes per value add 16 entries each and finish with a 4-step butterfly;
-//   3. the 16 group leaders PUSH the CTA's N sums into the receive buffer of every CTA of the
+//   3. lane r of each group PUSHES the CTA's sum of that value into the receive buffer of every CTA of the
 //      cluster with st.async (remote shared-memory store that signals the destination's
 //      mbarrier with its byte count);
 //   4. warp 0 of every CTA waits on its own mbarrier and adds the CL partials in a fixed order,
@@ -118,8 +136,9 @@ struct PushReducer {
         cluster_sync_all();  // every CTA of the cluster is resident and its mbarrier initialised
     }
     template <int N>
-    __device__ __forceinline__ void reduce(float (&a)[N]) {
+    __device__ __forceinline__ void reduce(float (&a)[N], int evt = 0, int prof_n = 64) {
         static_assert(N <= kRows, "accumulator too wide");
+        (void)evt; (void)prof_n;
         const int tid = threadIdx.x;
         // phase n uses receive buffer / mbarrier n & 1.  A peer can be at most one phase ahead, so a
         // push of phase n + 1 never lands in the mbarrier that still collects phase n.
@@ -129,6 +148,7 @@ struct PushReducer {
         if (tid == 0)  // arm this phase: N floats from each of the CL CTAs
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(N * CL * 4) : "memory");
         __syncthreads();
+        QEC_EVT(evt);
         const int v = tid >> 4, part = tid & 15;
         float s = 0.f;
         if (v < N) {
@@ -139,13 +159,15 @@ struct PushReducer {
                 s += (q.x + q.y) + (q.z + q.w);
             }
         }
+        if (evt == 2) QEC_EVT(22);
 #pragma unroll
         for (int d = 8; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-        if (v < N && part == 0) {
+        if (evt == 2) QEC_EVT(23);
+        if (v < N && part < CL) {  // every lane of the group holds the sum: lane r pushes to CTA r
             const unsigned slot = smem_u32(buf + ((phase & 1u) * CL + rank) * 16 + v);
-#pragma unroll
-            for (int r = 0; r < CL; ++r) st_async_f32(mapa_u32(slot, r), s, mapa_u32(mb, r));
+            st_async_f32(mapa_u32(slot, part), s, mapa_u32(mb, part));
         }
+        QEC_EVT(evt + 1);
         if (tid < 32) {
             const unsigned parity = (phase >> 1) & 1u;
             asm volatile(
@@ -154,6 +176,7 @@ struct PushReducer {
                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
                 "@!p bra WAIT_%=;\n\t}" ::"r"(mb), "r"(parity)
                 : "memory");
+            if (evt == 2) QEC_EVT(24);
             float t = 0.f;
             if (tid < 16) {
                 const float* b = buf + (phase & 1u) * CL * 16 + tid;
@@ -163,6 +186,7 @@ struct PushReducer {
 #pragma unroll
             for (int i = 0; i < N; ++i) a[i] = __shfl_sync(0xffffffffu, t, i);
         }
+        QEC_EVT(evt + 2);
         ++phase;
     }
     __device__ __forceinline__ bool solver() const { return threadIdx.x < 32; }
@@ -247,6 +271,15 @@ __device__ __forceinline__ void prefetch_slot(const PairGeom& G, const float* tc
     cp_async_commit();
 }
 
+// acc: M (10), [10] = sum |b|, [11] = sum b.  All 32 lanes of the solving warp hold the same sums,
+// so the convergence branch of the low-latency solver is uniform without a vote.
+__device__ __forceinline__ Quat solve_pose2(const float* acc, bool valid) {
+    const Sym4 m = acc_to_sym(acc, 1.f / fmaxf(acc[10], 1e-12f));  // F.normalize(p=1) of the weights
+    Quat p = qfix(top_eigvec_weighted2(m, acc[11] != acc[10], ThreadDone()));
+    if (!valid) p = qmake(0.f, 0.f, 0.f, 0.f);
+    return p;
+}
+
 template <int M>
 __device__ __forceinline__ void wait_slot() {  // slot M's group is complete (groups are committed in slot order)
     cp_async_wait<kPairs - 1 - M>();
@@ -299,6 +332,9 @@ __global__ void __launch_bounds__(kPT, 2)
 #pragma unroll
         for (int m = 0; m < kPairs; ++m) prefetch_slot<FULL>(G, tc, sA, sB, m);
     }
+#ifdef QEC_PROF
+    int prof_n = 0;
+#endif
     bool pend = false;       // the previous capsule's epilogue sums wait for this capsule's first reduction
     long long pend_c = 0;
     float e0 = 0.f, e1 = 0.f;
@@ -317,6 +353,7 @@ __global__ void __launch_bounds__(kPT, 2)
         const float* lrf_c = lrfs + ((size_t)bp * J + j_begin) * 4;
         const float* act_c = act + (size_t)bp * J + j_begin;
         // ---- sweep 0: votes from the prefetched transforms, M^0 = sum a v v^T, b^0 = a ----------
+        QEC_EVT(0);
         float acc[15];
         {
             f2 m2[10], ssum = bc(0.f), comp = bc(0.f);
@@ -362,16 +399,23 @@ __global__ void __launch_bounds__(kPT, 2)
             acc[13] = e0;
             acc[14] = e1;
         }
+        QEC_EVT(1);
+#ifdef QEC_PROF
+        red.reduce(acc, 2, prof_n);
+#else
         red.reduce(acc);
+#endif
         bool valid = false;
         float r[4] = {0.f, 0.f, 0.f, 0.f};
         if (red.solver()) {
             if (pend && writer) finish(pend_c, p, acc[13], acc[14]);
             valid = acc[12] != 0.f;  // reference qec_module.py:72-73
-            const Quat q = solve_pose(acc, valid);
+            const Quat q = solve_pose2(acc, valid);
             r[0] = q.w; r[1] = q.x; r[2] = q.y; r[3] = q.z;
         }
+        QEC_EVT(5);
         red.bcast(r);
+        QEC_EVT(6);
         p = qmake(r[0], r[1], r[2], r[3]);
         if (writer) stq(poses_all + (size_t)c * 4, p);
         // ---- sweeps 1..T-1: b <- b a (1 - d(pose, v)), M^t = sum b v v^T, all from shared memory
@@ -398,12 +442,19 @@ __global__ void __launch_bounds__(kPT, 2)
             for (int i = 0; i < 10; ++i) a2[i] = hsum(m2[i]);
             a2[10] = sabs;
             a2[11] = hsum(ssum);
+            QEC_EVT(7 * t);
+#ifdef QEC_PROF
+            red.reduce(a2, 7 * t + 1, prof_n);
+#else
             red.reduce(a2);
+#endif
             if (red.solver()) {
-                const Quat q = solve_pose(a2, valid);
+                const Quat q = solve_pose2(a2, valid);
                 r[0] = q.w; r[1] = q.x; r[2] = q.y; r[3] = q.z;
             }
+            QEC_EVT(7 * t + 4);
             red.bcast(r);
+            QEC_EVT(7 * t + 5);
             p = qmake(r[0], r[1], r[2], r[3]);
             if (writer) stq(poses_all + ((size_t)t * Nc + c) * 4, p);
         }
@@ -430,6 +481,8 @@ __global__ void __launch_bounds__(kPT, 2)
             e1 = en;
             pend = true;
             pend_c = c;
+            QEC_EVT(21);
+            QEC_EVT_NEXT();
         }
     }
     if (pend) {
@@ -531,6 +584,12 @@ extern "C" int qec_routing_fused_fwd(const float* t_oqi, const float* lrfs, cons
     QEC_DISPATCH_CL(launch_fused2_fwd, t_oqi, lrfs, act, alpha, beta, pose, agreement, poses_all, stats, Nc, K, I, O,
                     T, st)
 }
+
+#ifdef QEC_PROF
+extern "C" int qec_prof_read(long long* dst_host) {
+    return (int)cudaMemcpyFromSymbol(dst_host, qec::g_prof, sizeof(long long) * 8 * 64 * 32);
+}
+#endif
 
 extern "C" int qec_routing_fused_bwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
                                      const float* beta, const float* poses_all, const float* stats,

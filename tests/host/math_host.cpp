@@ -35,6 +35,16 @@ void h_top_eigvec_psd(int n, const float* M10, float* v, int* steps) {
     }
 }
 
+void h_top_eigvec_psd2(int n, const float* M10, float* v, int* rounds) {
+    for (int i = 0; i < n; ++i) {
+        Sym4 s = load_sym(M10 + 10 * i);
+        int cnt = 0;
+        Quat q = top_eigvec_psd2(s, [&cnt](bool d) { ++cnt; return d; });
+        v[4 * i + 0] = q.w; v[4 * i + 1] = q.x; v[4 * i + 2] = q.y; v[4 * i + 3] = q.z;
+        rounds[i] = cnt;
+    }
+}
+
 void h_jacobi_full(int n, const float* M10, float* w, float* Vout) {
     for (int i = 0; i < n; ++i) {
         Sym4 s = load_sym(M10 + 10 * i);

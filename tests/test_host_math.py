@@ -56,6 +56,33 @@ def test_jacobi_top_eigenvector(lib, spread, J):
     assert (err <= 1e-6 + 5e-7 / np.maximum(gap, 1e-12)).all()
 
 
+@pytest.mark.parametrize("fn", ["h_top_eigvec_psd", "h_top_eigvec_psd2"])
+@pytest.mark.parametrize("spread,J", [(0.1, 9), (0.5, 9), (3.0, 9), (100.0, 9), (0.3, 256), (100.0, 512)])
+def test_squaring_top_eigenvector(lib, fn, spread, J):
+    """the repeated-squaring solvers of the routing kernels (psd2 = the low-latency variant of the
+    packed cluster kernels) against float64 LAPACK, incl. the zero matrix and tiny / huge scales"""
+    rng = np.random.default_rng(int(spread * 10) + J + 1)
+    M = weighted_outer(4000, J, spread, rng)
+    M[0] = 0
+    M[1] *= 1e-30
+    M[2] *= 1e30
+    M10 = np.ascontiguousarray(M[:, IU[0], IU[1]])
+    n = len(M10)
+    v = np.zeros((n, 4), np.float32)
+    steps = np.zeros(n, np.int32)
+    getattr(lib, fn)(n, P(M10), P(v), P(steps))
+    w64, V64 = np.linalg.eigh(M.astype(np.float64))
+    top = V64[:, :, 3]
+    gap = (w64[:, 3] - w64[:, 2]) / np.maximum(w64[:, 3], 1e-300)
+    err = np.minimum(np.abs(v - top).max(-1), np.abs(v + top).max(-1))
+    assert np.array_equal(v[0], np.array([0, 0, 0, 1], np.float32))
+    assert np.abs(np.linalg.norm(v, axis=-1) - 1).max() < 1e-6
+    ok = err <= 1e-6 + 5e-7 / np.maximum(gap, 1e-12)
+    ok[0] = True
+    assert ok.all(), (err[~ok][:5], gap[~ok][:5])
+    assert steps.max() <= (13 if fn.endswith("2") else 26)
+
+
 def test_jacobi_full_decomposition_and_edge_cases(lib):
     rng = np.random.default_rng(3)
     A = rng.standard_normal((500, 4, 4))
