@@ -102,6 +102,28 @@ __device__ __forceinline__ Quat2 qham2(const Quat2& q, const Quat2& r) {
     return o;
 }
 
+// q (x) conj(r) and conj(q) (x) r for packed pairs (the two adjoint Hamilton products of vote_bwd)
+__device__ __forceinline__ Quat2 qham2_conjr(const Quat2& q, const Quat2& r) {
+    const f2 m1 = bc(-1.f);
+    const f2 nw = mul2(q.w, m1), nx = mul2(q.x, m1), ny = mul2(q.y, m1), nz = mul2(q.z, m1);
+    Quat2 o;
+    o.w = fma2(q.z, r.z, fma2(q.y, r.y, fma2(q.x, r.x, mul2(q.w, r.w))));
+    o.x = fma2(q.z, r.y, fma2(ny, r.z, fma2(q.x, r.w, mul2(nw, r.x))));
+    o.y = fma2(nz, r.x, fma2(q.y, r.w, fma2(q.x, r.z, mul2(nw, r.y))));
+    o.z = fma2(q.z, r.w, fma2(q.y, r.x, fma2(nx, r.y, mul2(nw, r.z))));
+    return o;
+}
+__device__ __forceinline__ Quat2 qham2_conjl(const Quat2& q, const Quat2& r) {
+    const f2 m1 = bc(-1.f);
+    const f2 nx = mul2(q.x, m1), ny = mul2(q.y, m1), nz = mul2(q.z, m1);
+    Quat2 o;
+    o.w = fma2(q.z, r.z, fma2(q.y, r.y, fma2(q.x, r.x, mul2(q.w, r.w))));
+    o.x = fma2(q.z, r.y, fma2(ny, r.z, fma2(nx, r.w, mul2(q.w, r.x))));
+    o.y = fma2(nz, r.x, fma2(ny, r.w, fma2(q.x, r.z, mul2(q.w, r.y))));
+    o.z = fma2(nz, r.w, fma2(q.y, r.x, fma2(nx, r.y, mul2(q.w, r.z))));
+    return o;
+}
+
 // 1 - d(x) for both halves; bit-identical per half to one_minus_dist (qec_math.cuh): the
 // polynomial is evaluated with negated coefficients so the final fma needs no negation.
 __device__ __forceinline__ f2 one_minus_dist2(f2 x) {
@@ -117,7 +139,16 @@ __device__ __forceinline__ f2 one_minus_dist2(f2 x) {
     const f2 s = pk(fsqrt_fast(lo(om)), fsqrt_fast(hi(om)));
     return fma2(s, p, bc(1.f));
 }
-__device__ __forceinline__ f2 dist_grad2(f2 x) { return pk(dist_grad(lo(x)), dist_grad(hi(x))); }
+// d/dx of d(x) for both halves: -(2/pi) sign(x) / sqrt(1 - x^2) where |x| <= 0.9999, else 0
+// (scalar twin: dist_grad).  sign(x) = clamp(x * 2^126, -1, 1) is exact for normal x.
+__device__ __forceinline__ f2 dist_grad2(f2 x) {
+    const f2 om = fma2(mul2(x, bc(-1.f)), x, bc(1.f));
+    const f2 g = mul2(pk(frsqrt(lo(om)), frsqrt(hi(om))), bc(-0.63661977236758f));
+    const f2 y = mul2(x, bc(8.507059173e37f));
+    const f2 r = mul2(g, pk(fminf(fmaxf(lo(y), -1.f), 1.f), fminf(fmaxf(hi(y), -1.f), 1.f)));
+    // select, not multiply-by-zero: |x| = 1 exactly (a capsule with one live vote) makes g infinite
+    return pk((fabsf(lo(x)) <= QEC_DCLAMP) ? lo(r) : 0.f, (fabsf(hi(x)) <= QEC_DCLAMP) ? hi(r) : 0.f);
+}
 
 // M += w v v^T for both halves: 4 FMUL2 + 10 FFMA2.  m[0..9] in acc_rank1 order.
 __device__ __forceinline__ void acc_rank1_2(f2* m, f2 w, const Quat2& v) {

@@ -553,6 +553,437 @@ static int launch_fused2_fwd(const float* t_oqi, const float* lrfs, const float*
     return e == cudaSuccess ? launch_status() : (int)e;
 }
 
+
+// ------------------------------------------------------------------------------------
+// backward (T <= kTB = 3), packed twin of routing_fused_bwd_kernel (routing_fused.cu; algebra in
+// routing_core.cuh / SURVEY.md App. B).  Levels t = T-1..0; sweep k completes level TT = T-k (its
+// adjoint vector u^TT is known from the previous reduction) and accumulates level TT-1.
+// Shared memory per pair: the two votes (32 B) and the cached 1 - d^t of the levels below the top
+// (16 B).  dL/db^TT is rebuilt per sweep from per-capsule registers by walking down from the top
+// level.  The transforms of the next capsule are prefetched into the vote slots during the last
+// sweep, as in the forward.
+// ------------------------------------------------------------------------------------
+struct Bwd2Caps {  // per-capsule state, registers
+    Quat ph[kTB], uh[kTB];
+    float rS[kTB];
+    float gsn;
+};
+
+// g = dL/dvote -> dL/dt_raw, dL/dlrf for a pair (scalar twin: vote_bwd in vote_math.cuh)
+__device__ __forceinline__ void vote_bwd2(const Quat2& lrf, const VotePair& vp, const Quat2& g, Quat2& g_traw,
+                                          Quat2& g_lrf) {
+    const Quat2 gh = qscale2(g, vp.sv);
+    g_lrf = qham2_conjr(gh, vp.t);                            // d(l (x) t)/dl = g (x) conj(t)
+    const Quat2 gt = qscale2(qham2_conjl(lrf, gh), vp.st);    // d(l (x) t)/dt = conj(l) (x) g, through the fix
+    // normalisation Jacobian (I - that that^T) / |t_raw|   (identity / eps if clamped)
+    const f2 d = qdot2(vp.that, gt);
+    const f2 proj = pk((lo(vp.rn) < 1e12f) ? lo(d) : 0.f, (hi(vp.rn) < 1e12f) ? hi(d) : 0.f);
+    const f2 np = mul2(proj, bc(-1.f));
+    g_traw.w = mul2(fma2(np, vp.that.w, gt.w), vp.rn);
+    g_traw.x = mul2(fma2(np, vp.that.x, gt.x), vp.rn);
+    g_traw.y = mul2(fma2(np, vp.that.y, gt.y), vp.rn);
+    g_traw.z = mul2(fma2(np, vp.that.z, gt.z), vp.rn);
+}
+
+// gradient w.r.t. b^TT (gb), running activation gradient (ga), b^t of all levels, <p^TT,v>, <u^TT,v>
+template <int T, int TT>
+__device__ __forceinline__ void complete_levels2(const Bwd2Caps& C, const Quat2& v, f2 a, f2 gate, f2 om0, f2 om1,
+                                                 f2& gb, f2& ga, f2& x_tt, f2& uv_tt, f2 (&b)[kTB]) {
+    b[0] = a;
+    b[1] = mul2(a, mul2(a, om0));
+    b[2] = mul2(b[1], mul2(a, om1));
+    gb = bc(0.f);
+    ga = bc(0.f);
+#pragma unroll
+    for (int t = T - 1; t >= TT; --t) {
+        const f2 x = qdot2(C.ph[t], v);
+        const f2 uv = qdot2(C.uh[t], v);
+        f2 direct;
+        if (t == T - 1) {
+            direct = mul2(bc(C.gsn), one_minus_dist2(x));
+        } else {
+            const f2 om = (t == 0) ? om0 : om1;        // cached 1 - d^t
+            ga = fma2(mul2(gb, b[t]), om, ga);         // b^{t+1} = b^t a (1 - d^t)
+            direct = mul2(mul2(gb, a), om);
+        }
+        // the M-path is gated by [a != 0]
+        gb = fma2(mul2(mul2(uv, x), gate), bc(C.rS[t]), direct);
+        if (t == TT) {
+            x_tt = x;
+            uv_tt = uv;
+        }
+    }
+}
+
+// element offsets (32-bit; qec_routing_fused_packed_supported bounds the tensor sizes) instead of
+// six 64-bit pointers: the bases stay in the kernel-parameter bank
+struct Bwd2Geom {
+    const float* act;
+    const float* lrfs;
+    const float* t_oqi;
+    float* g_toqi;
+    float* g_lrfs;   // nullable
+    float* g_act;    // nullable: no activation gradient -> only the top level is processed
+    unsigned offA;   // bp * J + j_begin: first vote of this CTA's slice in act / g_act (x4 in lrfs / g_lrfs)
+    unsigned offT;   // bp * K * trow + o * 4I: the capsule's block in t_oqi / g_toqi
+    int I, dko, di, wrap;  // pair walker: per slot j += 2 * kPT
+};
+
+// (k * trow + i) of the pair in slot m, advanced slot by slot (j += 2 * kPT) without a division
+struct OffWalk {
+    int off, i;
+    __device__ __forceinline__ void next(const Bwd2Geom& B) {
+        i += B.di;
+        off += B.dko;
+        if (i >= B.I) {
+            i -= B.I;
+            off += B.wrap;
+        }
+    }
+};
+
+template <bool FULL>
+__device__ __forceinline__ void prefetch_walk(const Bwd2Geom& B, unsigned offT_next, OffWalk& w, float4* sA, float4* sB,
+                                              int np, int m) {
+    const int ps = threadIdx.x + m * kPT;
+    if (FULL || ps < np) {
+        const float* tp = B.t_oqi + (size_t)(offT_next + (unsigned)w.off);
+        float* a = reinterpret_cast<float*>(sA + ps);
+        float* b = reinterpret_cast<float*>(sB + ps);
+        cp_async8(a, tp);
+        cp_async8(a + 2, tp + B.I);
+        cp_async8(b, tp + 2 * B.I);
+        cp_async8(b + 2, tp + 3 * B.I);
+    }
+    cp_async_commit();
+    w.next(B);
+}
+
+// ---- top level, pass 1: dL/dvote of the level whose votes are not detached -> dL/dt_raw, dL/dlrf.
+// No accumulators are live here; the accumulation of level T-2 is a separate pass (bwd2_acc_sweep),
+// which keeps both under the 128-register budget of two CTAs per SM.
+template <int T, bool FULL, bool PREFETCH>
+__device__ __forceinline__ void bwd2_grad_pass(int np, const Bwd2Geom& B, const Bwd2Caps& C, OffWalk w0, float4* sA,
+                                               float4* sB, unsigned offT_next) {
+    constexpr int TT = T - 1;
+    float2* som0 = reinterpret_cast<float2*>(sB + kNpMax);
+    float2* som1 = som0 + kNpMax;
+    OffWalk w = w0, wp = w0;
+#pragma unroll
+    for (int m = 0; m < kPairs; ++m) {
+        const int ps = threadIdx.x + m * kPT;
+        if (FULL || ps < np) {
+            // issued first: the level walk below hides their latency
+            const float* tp = B.t_oqi + (size_t)(B.offT + (unsigned)w.off);
+            Quat2 traw;
+            traw.w = ldg_f2(tp); traw.x = ldg_f2(tp + B.I); traw.y = ldg_f2(tp + 2 * B.I); traw.z = ldg_f2(tp + 3 * B.I);
+            const float* lp = B.lrfs + ((size_t)B.offA + 2 * ps) * 4;
+            const Quat2 lrf = pk(ldq_nc(lp), ldq_nc(lp + 4));
+            const f2 a = ldg_f2(B.act + (size_t)B.offA + 2 * ps);
+            const Quat2 v = lds_pair(sA, sB, ps);
+            f2 b = a;
+            if (T >= 2) b = mul2(b, mul2(a, lds_f2(som0 + ps)));
+            if (T >= 3) b = mul2(b, mul2(a, lds_f2(som1 + ps)));
+            const f2 x = qdot2(C.ph[TT], v);
+            const f2 uv = qdot2(C.uh[TT], v);
+            const f2 gx = mul2(mul2(bc(-C.gsn), b), dist_grad2(x));
+            const f2 wh = mul2(b, bc(C.rS[TT]));
+            Quat2 gv = qscale2(C.ph[TT], fma2(wh, uv, gx));  // p (gx + w <u,v>)
+            gv = qfma2(mul2(wh, x), C.uh[TT], gv);           // + u w <p,v>
+            const VotePair vp = make_vote2<true>(lrf, traw);
+            Quat2 gt, gq;
+            vote_bwd2(lrf, vp, gv, gt, gq);
+            float* gp = B.g_toqi + (size_t)(B.offT + (unsigned)w.off);
+            *reinterpret_cast<float2*>(gp) = make_float2(lo(gt.w), hi(gt.w));
+            *reinterpret_cast<float2*>(gp + B.I) = make_float2(lo(gt.x), hi(gt.x));
+            *reinterpret_cast<float2*>(gp + 2 * B.I) = make_float2(lo(gt.y), hi(gt.y));
+            *reinterpret_cast<float2*>(gp + 3 * B.I) = make_float2(lo(gt.z), hi(gt.z));
+            if (B.g_lrfs != nullptr) {  // sum over the O capsules of the patch
+                float* glp = B.g_lrfs + ((size_t)B.offA + 2 * ps) * 4;
+                red_add_q(glp, lo(gq));
+                red_add_q(glp + 4, hi(gq));
+            }
+        }
+        w.next(B);
+        if (PREFETCH) prefetch_walk<FULL>(B, offT_next, wp, sA, sB, np, m);
+    }
+}
+
+// ---- sweep that completes level TT (u^TT known) and accumulates level TT-1 (chain only)
+template <int T, int TT, bool FULL, bool PREFETCH>
+__device__ __forceinline__ void bwd2_acc_sweep(int np, const Bwd2Geom& B, const Bwd2Caps& C, OffWalk w0, float4* sA,
+                                               float4* sB, unsigned offT_next, float (&acc)[15]) {
+    float2* som0 = reinterpret_cast<float2*>(sB + kNpMax);
+    float2* som1 = som0 + kNpMax;
+    f2 a2[14];
+#pragma unroll
+    for (int i = 0; i < 14; ++i) a2[i] = bc(0.f);
+    float sabs = 0.f;
+    OffWalk wp = w0;
+    auto lda = [&](int m, f2& a) {  // activations run one slot ahead (L2-resident: shared by all O)
+        const int ps = threadIdx.x + m * kPT;
+        if (FULL || ps < np) a = ldg_f2(B.act + (size_t)B.offA + 2 * ps);
+    };
+    f2 an[2];
+    lda(0, an[0]);
+#pragma unroll
+    for (int m = 0; m < kPairs; ++m) {
+        if (m + 1 < kPairs) lda(m + 1, an[(m + 1) & 1]);
+        const int ps = threadIdx.x + m * kPT;
+        if (FULL || ps < np) {
+            const f2 a = an[m & 1];
+            const Quat2 v = lds_pair(sA, sB, ps);
+            const f2 om0 = (T >= 2) ? lds_f2(som0 + ps) : bc(1.f);
+            const f2 om1 = (T >= 3) ? lds_f2(som1 + ps) : bc(1.f);
+            const f2 gate = pk((lo(a) != 0.f) ? 1.f : 0.f, (hi(a) != 0.f) ? 1.f : 0.f);
+            f2 gb, ga, x, uv, b[kTB];
+            complete_levels2<T, TT>(C, v, a, gate, om0, om1, gb, ga, x, uv, b);
+            if (TT >= 1) {  // level TT-1: dL/dd_j = -g_b^TT b^{TT-1} a
+                const f2 xl = qdot2(C.ph[TT >= 1 ? TT - 1 : 0], v);
+                const f2 bl = b[TT >= 1 ? TT - 1 : 0];
+                const f2 gx = mul2(mul2(mul2(gb, bc(-1.f)), mul2(bl, a)), dist_grad2(xl));
+                a2[0] = fma2(gx, v.w, a2[0]); a2[1] = fma2(gx, v.x, a2[1]);
+                a2[2] = fma2(gx, v.y, a2[2]); a2[3] = fma2(gx, v.z, a2[3]);
+                acc_rank1_2(a2 + 4, bl, v);
+                sabs = (sabs + fabsf(lo(bl))) + fabsf(hi(bl));
+            }
+            if (TT == 0) {  // + dL/db^0 (b^0 = a)
+                const f2 g2 = add2(ga, gb);
+                asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(B.g_act + (size_t)B.offA + 2 * ps),
+                             "f"(lo(g2)), "f"(hi(g2))
+                             : "memory");
+            }
+        }
+        if (PREFETCH) prefetch_walk<FULL>(B, offT_next, wp, sA, sB, np, m);
+    }
+#pragma unroll
+    for (int i = 0; i < 14; ++i) acc[i] = hsum(a2[i]);
+    acc[14] = sabs;
+}
+
+// sweep 0: generate the votes (from the prefetched transforms), cache 1 - d^t of the levels below the
+// top, accumulate level T-1
+template <int T, bool FULL>
+__device__ __forceinline__ void bwd2_sweep0(int np, const Bwd2Geom& B, const Bwd2Caps& C, float4* sA, float4* sB,
+                                            float (&acc)[15]) {
+    float2* som0 = reinterpret_cast<float2*>(sB + kNpMax);
+    float2* som1 = som0 + kNpMax;
+    f2 a2[14];
+#pragma unroll
+    for (int i = 0; i < 14; ++i) a2[i] = bc(0.f);
+    float sabs = 0.f;
+    auto ldl = [&](int m, Quat2& lrf, f2& a) {
+        const int ps = threadIdx.x + m * kPT;
+        if (FULL || ps < np) {
+            const float* lp = B.lrfs + ((size_t)B.offA + 2 * ps) * 4;
+            lrf = pk(ldq_nc(lp), ldq_nc(lp + 4));
+            a = ldg_f2(B.act + (size_t)B.offA + 2 * ps);
+        }
+    };
+    auto gen = [&](int m, const Quat2& lrf, f2 a) {
+        const int ps = threadIdx.x + m * kPT;
+        const Quat2 traw = lds_pair(sA, sB, ps);
+        const Quat2 v = make_vote2<false>(lrf, traw).vote;
+        sts_pair(sA, sB, ps, v);
+        f2 b = a;
+        if (T >= 2) {
+            const f2 om = one_minus_dist2(qdot2(C.ph[0], v));
+            sts_f2(som0 + ps, om);
+            b = mul2(b, mul2(a, om));
+        }
+        if (T >= 3) {
+            const f2 om = one_minus_dist2(qdot2(C.ph[1], v));
+            sts_f2(som1 + ps, om);
+            b = mul2(b, mul2(a, om));
+        }
+        // level T-1 (final distance): dL/dd_j = -gsn b^{T-1}_j
+        const f2 gx = mul2(mul2(bc(-C.gsn), b), dist_grad2(qdot2(C.ph[T - 1], v)));
+        a2[0] = fma2(gx, v.w, a2[0]); a2[1] = fma2(gx, v.x, a2[1]);
+        a2[2] = fma2(gx, v.y, a2[2]); a2[3] = fma2(gx, v.z, a2[3]);
+        acc_rank1_2(a2 + 4, b, v);
+        sabs = (sabs + fabsf(lo(b))) + fabsf(hi(b));
+    };
+    Quat2 lr[3];
+    f2 av[3];
+    ldl(0, lr[0], av[0]);
+    ldl(1, lr[1], av[1]);
+#define QEC_GEN_SLOT(M)                                                       \
+    if ((M) + 2 < kPairs) ldl((M) + 2, lr[((M) + 2) % 3], av[((M) + 2) % 3]); \
+    wait_slot<(M)>();                                                         \
+    if (FULL || (threadIdx.x + (M) * kPT < np)) gen((M), lr[(M) % 3], av[(M) % 3]);
+    QEC_GEN_SLOT(0) QEC_GEN_SLOT(1) QEC_GEN_SLOT(2) QEC_GEN_SLOT(3)
+    QEC_GEN_SLOT(4) QEC_GEN_SLOT(5) QEC_GEN_SLOT(6) QEC_GEN_SLOT(7)
+#undef QEC_GEN_SLOT
+#pragma unroll
+    for (int i = 0; i < 14; ++i) acc[i] = hsum(a2[i]);
+    acc[14] = sabs;
+}
+
+template <int CL, bool FULL>
+__global__ void __launch_bounds__(kPT, 2)
+    routing_fused2_bwd_kernel(const float* __restrict__ t_oqi, const float* __restrict__ lrfs,
+                              const float* __restrict__ act, const float* __restrict__ alpha_p,
+                              const float* __restrict__ beta_p, const float* __restrict__ poses_all,
+                              const float* __restrict__ stats, const float* __restrict__ g_pose,
+                              const float* __restrict__ g_agr, float* __restrict__ g_toqi, float* g_lrfs, float* g_act,
+                              float* g_alpha_beta, long long Nc, int K, int I, int O, int T) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* __restrict__ sA = reinterpret_cast<float4*>(smem_raw);
+    float4* __restrict__ sB = sA + kNpMax;
+    unsigned rank;
+    asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    PushReducer<CL> red(reinterpret_cast<float*>(smem_raw + (2 * sizeof(float4) + 2 * sizeof(float2)) * kNpMax), rank);
+    const long long cid = blockIdx.x / CL, ncl = gridDim.x / CL;
+    const int J = K * I;
+    const int Jc = 2 * ((J / 2 + CL - 1) / CL);
+    const int j_begin = min(J, (int)rank * Jc);
+    const int nloc = min(J, j_begin + Jc) - j_begin;
+    const int np = nloc / 2;
+    const float alpha = __ldg(alpha_p), beta = __ldg(beta_p);
+    const unsigned trow = 4u * I * O;
+    const bool need_chain = g_act != nullptr;
+    float ga_tot = 0.f, gb_tot = 0.f;
+
+    Bwd2Geom B;
+    B.act = act; B.lrfs = lrfs; B.t_oqi = t_oqi; B.g_toqi = g_toqi; B.g_lrfs = g_lrfs; B.g_act = g_act;
+    B.I = I;
+    {
+        const int step = 2 * kPT, dk = step / I;
+        B.di = step - dk * I;
+        B.dko = dk * (int)trow + B.di;
+        B.wrap = (int)trow - I;
+    }
+    OffWalk w0;
+    {
+        const int j = j_begin + 2 * threadIdx.x;
+        const int k = j / I;
+        w0.i = j - k * I;
+        w0.off = k * (int)trow + w0.i;
+    }
+    auto offT_of = [&](long long c) {
+        const long long bp = c / O;
+        const int o = (int)(c - bp * O);
+        return (unsigned)bp * (unsigned)K * trow + (unsigned)o * 4u * (unsigned)I;
+    };
+    if (cid < Nc) {
+        OffWalk w = w0;
+        const unsigned o0 = offT_of(cid);
+#pragma unroll
+        for (int m = 0; m < kPairs; ++m) prefetch_walk<FULL>(B, o0, w, sA, sB, np, m);
+    }
+
+    for (long long c = cid; c < Nc; c += ncl) {
+        const long long bp = c / O;
+        B.offA = (unsigned)bp * (unsigned)J + (unsigned)j_begin;
+        B.offT = offT_of(c);
+        const long long cn = c + ncl;
+        const bool more = cn < Nc;
+        const unsigned offT_next = more ? offT_of(cn) : 0u;
+        Bwd2Caps C;
+#pragma unroll
+        for (int t = 0; t < kTB; ++t) {
+            C.ph[t] = (t < T) ? ldq_nc(poses_all + ((size_t)t * Nc + c) * 4) : qmake(0.f, 0.f, 0.f, 0.f);
+            C.uh[t] = qmake(0.f, 0.f, 0.f, 0.f);
+            C.rS[t] = 0.f;
+        }
+        const float s = __ldg(stats + 2 * c), n = __ldg(stats + 2 * c + 1);
+        const bool has = n > 0.f;
+        const float sg = sigmoidf(fmaf(alpha, s, beta - 1.f));
+        const float gz = has ? __ldg(g_agr + c) * sg * (1.f - sg) : 0.f;
+        ga_tot += gz * s;
+        gb_tot += gz;
+        C.gsn = has ? gz * alpha / n : 0.f;
+        const Quat gpose = ldq_nc(g_pose + (size_t)c * 4);
+
+        float acc[15];
+        if (T == 3) bwd2_sweep0<3, FULL>(np, B, C, sA, sB, acc);
+        else if (T == 2) bwd2_sweep0<2, FULL>(np, B, C, sA, sB, acc);
+        else bwd2_sweep0<1, FULL>(np, B, C, sA, sB, acc);
+
+        const int nsweeps = need_chain ? T : 1;
+        for (int k = 1; k <= nsweeps; ++k) {
+            const int t = T - k;  // level being completed
+            red.reduce(acc);      // sums of the level accumulated by the previous sweep
+            float r[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+            if (red.solver()) {
+                Quat p = C.ph[0];
+#pragma unroll
+                for (int u = 1; u < kTB; ++u)
+                    if (u == t) p = C.ph[u];
+                const float rs = 1.f / fmaxf(acc[14], 1e-12f);
+                const Sym4 m = acc_to_sym(acc + 4, rs);
+                Quat gp = qmake(acc[0], acc[1], acc[2], acc[3]);
+                if (t == T - 1) gp = qadd(gp, gpose);
+                const float lam = qdot(p, sym_mul(m, p));
+                Quat u = top_eigvec_adjoint(m, p, lam, gp);
+                if (!(qdot(p, p) > 0.5f)) u = qmake(0.f, 0.f, 0.f, 0.f);  // invalid / sign-zeroed pose
+                r[0] = u.w; r[1] = u.x; r[2] = u.y; r[3] = u.z; r[4] = rs;
+            }
+            red.bcast(r);
+#pragma unroll
+            for (int u = 0; u < kTB; ++u)
+                if (u == t) {
+                    C.uh[u] = qmake(r[0], r[1], r[2], r[3]);
+                    C.rS[u] = r[4];
+                }
+            // the votes die with the last pass over them: that pass refills the slots for the next capsule
+            const bool pf_grad = more && !need_chain;
+            const bool pf_acc = more && (k == nsweeps);
+#define QEC_BWD_GRAD(T_)                                                                       \
+    if (pf_grad) bwd2_grad_pass<T_, FULL, true>(np, B, C, w0, sA, sB, offT_next);              \
+    else bwd2_grad_pass<T_, FULL, false>(np, B, C, w0, sA, sB, offT_next);
+#define QEC_BWD_ACC(TT_, T_)                                                                   \
+    if (pf_acc) bwd2_acc_sweep<T_, TT_, FULL, true>(np, B, C, w0, sA, sB, offT_next, acc);     \
+    else bwd2_acc_sweep<T_, TT_, FULL, false>(np, B, C, w0, sA, sB, offT_next, acc);
+            switch (T * 4 + t) {
+                case 3 * 4 + 2: QEC_BWD_GRAD(3) if (need_chain) { QEC_BWD_ACC(2, 3) } break;
+                case 3 * 4 + 1: QEC_BWD_ACC(1, 3) break;
+                case 3 * 4 + 0: QEC_BWD_ACC(0, 3) break;
+                case 2 * 4 + 1: QEC_BWD_GRAD(2) if (need_chain) { QEC_BWD_ACC(1, 2) } break;
+                case 2 * 4 + 0: QEC_BWD_ACC(0, 2) break;
+                default: QEC_BWD_GRAD(1) if (need_chain) { QEC_BWD_ACC(0, 1) } break;
+            }
+#undef QEC_BWD_GRAD
+#undef QEC_BWD_ACC
+        }
+        // the next capsule's sweep 0 touches this thread's own slots only; the reducer's scratch is
+        // protected by the barriers inside reduce() / bcast()
+    }
+    if (rank == 0 && threadIdx.x == 0) {
+        atomicAdd(g_alpha_beta, ga_tot);
+        atomicAdd(g_alpha_beta + 1, gb_tot);
+    }
+    cluster_sync_all();
+}
+
+template <int CL>
+static int launch_fused2_bwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
+                             const float* beta, const float* poses_all, const float* stats, const float* g_pose,
+                             const float* g_agr, float* g_toqi, float* g_lrfs, float* g_act, float* g_ab, long long Nc,
+                             int K, int I, int O, int T, cudaStream_t st) {
+    const bool full = ((long long)K * I == (long long)CL * 2 * kNpMax);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    static int cached[2] = {-1, -1};
+    cudaError_t e;
+    if (full) {
+        auto kern = routing_fused2_bwd_kernel<CL, true>;
+        const int rc = fused2_grid(kern, CL, fwd2_smem<CL>(), Nc, cfg, attr, cached[1]);
+        if (rc) return rc;
+        cfg.stream = st;
+        e = cudaLaunchKernelEx(&cfg, kern, t_oqi, lrfs, act, alpha, beta, poses_all, stats, g_pose, g_agr, g_toqi,
+                               g_lrfs, g_act, g_ab, Nc, K, I, O, T);
+    } else {
+        auto kern = routing_fused2_bwd_kernel<CL, false>;
+        const int rc = fused2_grid(kern, CL, fwd2_smem<CL>(), Nc, cfg, attr, cached[0]);
+        if (rc) return rc;
+        cfg.stream = st;
+        e = cudaLaunchKernelEx(&cfg, kern, t_oqi, lrfs, act, alpha, beta, poses_all, stats, g_pose, g_agr, g_toqi,
+                               g_lrfs, g_act, g_ab, Nc, K, I, O, T);
+    }
+    return e == cudaSuccess ? launch_status() : (int)e;
+}
+
 }  // namespace qec
 
 using namespace qec;
@@ -596,6 +1027,18 @@ extern "C" int qec_routing_fused_bwd(const float* t_oqi, const float* lrfs, cons
                                      const float* g_pose, const float* g_agreement, float* g_toqi, float* g_lrfs,
                                      float* g_act, float* g_alpha_beta, int BP, int K, int I, int O, int T,
                                      void* stream) {
-    return qec_routing_fused_bwd_scalar(t_oqi, lrfs, act, alpha, beta, poses_all, stats, g_pose, g_agreement, g_toqi,
-                                        g_lrfs, g_act, g_alpha_beta, BP, K, I, O, T, stream);
+    if (!qec_routing_fused_packed_supported(K, I, O, T))
+        return qec_routing_fused_bwd_scalar(t_oqi, lrfs, act, alpha, beta, poses_all, stats, g_pose, g_agreement,
+                                            g_toqi, g_lrfs, g_act, g_alpha_beta, BP, K, I, O, T, stream);
+    QEC_CHECK_ARG(t_oqi, 1);
+    QEC_CHECK_ARG(lrfs, 2);
+    QEC_CHECK_ARG(act && alpha && beta && poses_all && stats, 3);
+    QEC_CHECK_ARG(g_pose && g_agreement, 8);
+    QEC_CHECK_ARG(g_toqi && g_alpha_beta, 10);
+    QEC_CHECK_ARG(BP > 0, 14);
+    const int CL = pick_cluster(K * I);
+    const long long Nc = (long long)BP * O;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    QEC_DISPATCH_CL(launch_fused2_bwd, t_oqi, lrfs, act, alpha, beta, poses_all, stats, g_pose, g_agreement, g_toqi,
+                    g_lrfs, g_act, g_alpha_beta, Nc, K, I, O, T, st)
 }

@@ -63,7 +63,7 @@ for (BP, K, I, O, T) in shapes:
             ga = bwd("qec_routing_fused_bwd", t, lrfs, act, BP, K, I, O, T, b, chain=chain)
             gb = bwd("qec_routing_fused_bwd_scalar", t, lrfs, act, BP, K, I, O, T, b, chain=chain)
             e2 = [rel(x, y) for x, y in zip(ga, gb)]
-            line += " | bwd%s g_t %.2e g_l %.2e g_a %.2e g_ab %.2e" % (("" if chain else "(nochain)"),) + tuple(e2)
+            line += " | bwd%s g_t %.2e g_l %.2e g_a %.2e g_ab %.2e" % ((("" if chain else "(nochain)"),) + tuple(e2))
             worst = max(worst, *[e for e in e2 if e == e])
     print((BP, K, I, O, T), line)
 print("WORST", worst)
