@@ -231,7 +231,7 @@ def run_b200(a):
     net = qb.QecNet(2048, a.channels, a.classes, a.iters).to(dev)
     ddp.broadcast_parameters(net, 0)
     bucket = ddp.FlatGradBucket(net.parameters())
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=True)  # train_cls.py:44-51
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=True, fused=True)  # train_cls.py:44-51 (one fused kernel)
 
     NB = 4  # distinct batches rotated through the timed region
     host = [synthetic_batch(a.batch, ncls=a.classes, seed=1234 + 1000 * rank + i, pin=True) for i in range(NB)]

@@ -205,6 +205,12 @@ struct PushReducer {
     __device__ __forceinline__ void sync() { __syncthreads(); }
 };
 
+// round-to-nearest onto the TF32 grid (10-bit mantissa), both halves; the result is exactly representable
+__device__ __forceinline__ f2 tf32_round2(f2 v) {
+    const unsigned a = (__float_as_uint(lo(v)) + 0x1000u) & 0xffffe000u, b = (__float_as_uint(hi(v)) + 0x1000u) & 0xffffe000u;
+    return pk(__uint_as_float(a), __uint_as_float(b));
+}
+
 // two votes at once (reference models/qec_module.py:129-145, scalar twin: make_vote in vote_math.cuh)
 struct VotePair {
     Quat2 vote;
@@ -495,7 +501,7 @@ __global__ void __launch_bounds__(kPT, 2)
 
 template <int CL>
 constexpr size_t fwd2_smem() {
-    return (2 * sizeof(float4) + 2 * sizeof(float2)) * kNpMax + sizeof(float) * PushReducer<CL>::kSmemFloats;
+    return (2 * sizeof(float4) + 2 * sizeof(float2)) * kNpMax + sizeof(float) * (PushReducer<CL>::kSmemFloats + 32);
 }
 
 // like fused_grid (routing_fused_shared.cuh) but the cluster attribute is set for CL = 1 too: the
@@ -622,6 +628,7 @@ struct Bwd2Geom {
     const float* lrfs;
     const float* t_oqi;
     float* g_toqi;
+    float* g_lo;     // nullable: if set, g_toqi receives the TF32-rounded gradient and g_lo the remainder
     float* g_lrfs;   // nullable
     float* g_act;    // nullable: no activation gradient -> only the top level is processed
     unsigned offA;   // bp * J + j_begin: first vote of this CTA's slice in act / g_act (x4 in lrfs / g_lrfs)
@@ -669,7 +676,7 @@ __device__ __forceinline__ void bwd2_grad_pass(int np, const Bwd2Geom& B, const 
     float2* som0 = reinterpret_cast<float2*>(sB + kNpMax);
     float2* som1 = som0 + kNpMax;
     OffWalk w = w0, wp = w0;
-#pragma unroll
+#pragma unroll 1  // one pair in flight: ~70 live registers per pair leave no room to overlap two
     for (int m = 0; m < kPairs; ++m) {
         const int ps = threadIdx.x + m * kPT;
         if (FULL || ps < np) {
@@ -694,6 +701,19 @@ __device__ __forceinline__ void bwd2_grad_pass(int np, const Bwd2Geom& B, const 
             Quat2 gt, gq;
             vote_bwd2(lrf, vp, gv, gt, gq);
             float* gp = B.g_toqi + (size_t)(B.offT + (unsigned)w.off);
+            if (B.g_lo != nullptr) {
+                // pre-split for the tensor-core GEMMs that consume it (quater_gen2's backward at FP32
+                // accuracy): hi on the TF32 grid (an exact tensor-core input), lo = g - hi exactly
+                float* gq2 = B.g_lo + (size_t)(B.offT + (unsigned)w.off);
+                const f2 hw = tf32_round2(gt.w), hx = tf32_round2(gt.x), hy = tf32_round2(gt.y), hz = tf32_round2(gt.z);
+                const f2 lw = fma2(hw, bc(-1.f), gt.w), lx = fma2(hx, bc(-1.f), gt.x), ly = fma2(hy, bc(-1.f), gt.y),
+                         lz = fma2(hz, bc(-1.f), gt.z);
+                *reinterpret_cast<float2*>(gq2) = make_float2(lo(lw), hi(lw));
+                *reinterpret_cast<float2*>(gq2 + B.I) = make_float2(lo(lx), hi(lx));
+                *reinterpret_cast<float2*>(gq2 + 2 * B.I) = make_float2(lo(ly), hi(ly));
+                *reinterpret_cast<float2*>(gq2 + 3 * B.I) = make_float2(lo(lz), hi(lz));
+                gt.w = hw; gt.x = hx; gt.y = hy; gt.z = hz;
+            }
             *reinterpret_cast<float2*>(gp) = make_float2(lo(gt.w), hi(gt.w));
             *reinterpret_cast<float2*>(gp + B.I) = make_float2(lo(gt.x), hi(gt.x));
             *reinterpret_cast<float2*>(gp + 2 * B.I) = make_float2(lo(gt.y), hi(gt.y));
@@ -825,14 +845,16 @@ __global__ void __launch_bounds__(kPT, 2)
                               const float* __restrict__ act, const float* __restrict__ alpha_p,
                               const float* __restrict__ beta_p, const float* __restrict__ poses_all,
                               const float* __restrict__ stats, const float* __restrict__ g_pose,
-                              const float* __restrict__ g_agr, float* __restrict__ g_toqi, float* g_lrfs, float* g_act,
-                              float* g_alpha_beta, long long Nc, int K, int I, int O, int T) {
+                              const float* __restrict__ g_agr, float* __restrict__ g_toqi, float* g_lo, float* g_lrfs,
+                              float* g_act, float* g_alpha_beta, long long Nc, int K, int I, int O, int T) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* __restrict__ sA = reinterpret_cast<float4*>(smem_raw);
     float4* __restrict__ sB = sA + kNpMax;
     unsigned rank;
     asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-    PushReducer<CL> red(reinterpret_cast<float*>(smem_raw + (2 * sizeof(float4) + 2 * sizeof(float2)) * kNpMax), rank);
+    float* red_base = reinterpret_cast<float*>(smem_raw + (2 * sizeof(float4) + 2 * sizeof(float2)) * kNpMax);
+    PushReducer<CL> red(red_base, rank);
+    float* capsS = red_base + PushReducer<CL>::kSmemFloats;  // [kTB][8]: u^t (4), 1/S^t
     const long long cid = blockIdx.x / CL, ncl = gridDim.x / CL;
     const int J = K * I;
     const int Jc = 2 * ((J / 2 + CL - 1) / CL);
@@ -845,7 +867,7 @@ __global__ void __launch_bounds__(kPT, 2)
     float ga_tot = 0.f, gb_tot = 0.f;
 
     Bwd2Geom B;
-    B.act = act; B.lrfs = lrfs; B.t_oqi = t_oqi; B.g_toqi = g_toqi; B.g_lrfs = g_lrfs; B.g_act = g_act;
+    B.act = act; B.lrfs = lrfs; B.t_oqi = t_oqi; B.g_toqi = g_toqi; B.g_lo = g_lo; B.g_lrfs = g_lrfs; B.g_act = g_act;
     B.I = I;
     {
         const int step = 2 * kPT, dk = step / I;
@@ -879,69 +901,79 @@ __global__ void __launch_bounds__(kPT, 2)
         const long long cn = c + ncl;
         const bool more = cn < Nc;
         const unsigned offT_next = more ? offT_of(cn) : 0u;
-        Bwd2Caps C;
-#pragma unroll
-        for (int t = 0; t < kTB; ++t) {
-            C.ph[t] = (t < T) ? ldq_nc(poses_all + ((size_t)t * Nc + c) * 4) : qmake(0.f, 0.f, 0.f, 0.f);
-            C.uh[t] = qmake(0.f, 0.f, 0.f, 0.f);
-            C.rS[t] = 0.f;
-        }
+        // Per-capsule state lives in memory between sweeps, not in registers: the poses are re-read from
+        // poses_all (L2) and the adjoint vectors u^t / 1/S^t from a 32-float shared array, so that each
+        // sweep only keeps what it uses live (the 28 registers of the full state made the sweeps spill).
         const float s = __ldg(stats + 2 * c), n = __ldg(stats + 2 * c + 1);
         const bool has = n > 0.f;
         const float sg = sigmoidf(fmaf(alpha, s, beta - 1.f));
         const float gz = has ? __ldg(g_agr + c) * sg * (1.f - sg) : 0.f;
         ga_tot += gz * s;
         gb_tot += gz;
-        C.gsn = has ? gz * alpha / n : 0.f;
-        const Quat gpose = ldq_nc(g_pose + (size_t)c * 4);
+        const float gsn = has ? gz * alpha / n : 0.f;
+        auto caps = [&](int t_lo, int u_lo) {  // poses of levels >= t_lo, adjoints of levels >= u_lo
+            Bwd2Caps C;
+#pragma unroll
+            for (int t = 0; t < kTB; ++t) {
+                C.ph[t] = (t < T && t >= t_lo) ? ldq_nc(poses_all + ((size_t)t * Nc + c) * 4) : qmake(0.f, 0.f, 0.f, 0.f);
+                const bool hu = (t < T && t >= u_lo);
+                C.uh[t] = hu ? qmake(capsS[t * 8], capsS[t * 8 + 1], capsS[t * 8 + 2], capsS[t * 8 + 3])
+                             : qmake(0.f, 0.f, 0.f, 0.f);
+                C.rS[t] = hu ? capsS[t * 8 + 4] : 0.f;
+            }
+            C.gsn = gsn;
+            return C;
+        };
 
         float acc[15];
-        if (T == 3) bwd2_sweep0<3, FULL>(np, B, C, sA, sB, acc);
-        else if (T == 2) bwd2_sweep0<2, FULL>(np, B, C, sA, sB, acc);
-        else bwd2_sweep0<1, FULL>(np, B, C, sA, sB, acc);
+        {
+            const Bwd2Caps C = caps(0, kTB);
+            if (T == 3) bwd2_sweep0<3, FULL>(np, B, C, sA, sB, acc);
+            else if (T == 2) bwd2_sweep0<2, FULL>(np, B, C, sA, sB, acc);
+            else bwd2_sweep0<1, FULL>(np, B, C, sA, sB, acc);
+        }
 
         const int nsweeps = need_chain ? T : 1;
         for (int k = 1; k <= nsweeps; ++k) {
             const int t = T - k;  // level being completed
             red.reduce(acc);      // sums of the level accumulated by the previous sweep
-            float r[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
             if (red.solver()) {
-                Quat p = C.ph[0];
-#pragma unroll
-                for (int u = 1; u < kTB; ++u)
-                    if (u == t) p = C.ph[u];
+                const Quat p = ldq_nc(poses_all + ((size_t)t * Nc + c) * 4);
                 const float rs = 1.f / fmaxf(acc[14], 1e-12f);
                 const Sym4 m = acc_to_sym(acc + 4, rs);
                 Quat gp = qmake(acc[0], acc[1], acc[2], acc[3]);
-                if (t == T - 1) gp = qadd(gp, gpose);
+                if (t == T - 1) gp = qadd(gp, ldq_nc(g_pose + (size_t)c * 4));
                 const float lam = qdot(p, sym_mul(m, p));
                 Quat u = top_eigvec_adjoint(m, p, lam, gp);
                 if (!(qdot(p, p) > 0.5f)) u = qmake(0.f, 0.f, 0.f, 0.f);  // invalid / sign-zeroed pose
-                r[0] = u.w; r[1] = u.x; r[2] = u.y; r[3] = u.z; r[4] = rs;
-            }
-            red.bcast(r);
-#pragma unroll
-            for (int u = 0; u < kTB; ++u)
-                if (u == t) {
-                    C.uh[u] = qmake(r[0], r[1], r[2], r[3]);
-                    C.rS[u] = r[4];
+                if (threadIdx.x == 0) {
+                    capsS[t * 8] = u.w; capsS[t * 8 + 1] = u.x; capsS[t * 8 + 2] = u.y; capsS[t * 8 + 3] = u.z;
+                    capsS[t * 8 + 4] = rs;
                 }
+            }
+            red.sync();  // u^t, 1/S^t visible to the CTA; the reducer's scratch may be reused
             // the votes die with the last pass over them: that pass refills the slots for the next capsule
             const bool pf_grad = more && !need_chain;
             const bool pf_acc = more && (k == nsweeps);
 #define QEC_BWD_GRAD(T_)                                                                       \
-    if (pf_grad) bwd2_grad_pass<T_, FULL, true>(np, B, C, w0, sA, sB, offT_next);              \
-    else bwd2_grad_pass<T_, FULL, false>(np, B, C, w0, sA, sB, offT_next);
+    {                                                                                          \
+        const Bwd2Caps C = caps(T_ - 1, T_ - 1);                                               \
+        if (pf_grad) bwd2_grad_pass<T_, FULL, true>(np, B, C, w0, sA, sB, offT_next);          \
+        else bwd2_grad_pass<T_, FULL, false>(np, B, C, w0, sA, sB, offT_next);                 \
+    }
 #define QEC_BWD_ACC(TT_, T_)                                                                   \
-    if (pf_acc) bwd2_acc_sweep<T_, TT_, FULL, true>(np, B, C, w0, sA, sB, offT_next, acc);     \
-    else bwd2_acc_sweep<T_, TT_, FULL, false>(np, B, C, w0, sA, sB, offT_next, acc);
+    {                                                                                          \
+        const Bwd2Caps C = caps(TT_ >= 1 ? TT_ - 1 : 0, TT_);                                  \
+        if (pf_acc) bwd2_acc_sweep<T_, TT_, FULL, true>(np, B, C, w0, sA, sB, offT_next, acc); \
+        else bwd2_acc_sweep<T_, TT_, FULL, false>(np, B, C, w0, sA, sB, offT_next, acc);       \
+    }
             switch (T * 4 + t) {
-                case 3 * 4 + 2: QEC_BWD_GRAD(3) if (need_chain) { QEC_BWD_ACC(2, 3) } break;
+                case 3 * 4 + 2: QEC_BWD_GRAD(3) if (need_chain) QEC_BWD_ACC(2, 3) break;
                 case 3 * 4 + 1: QEC_BWD_ACC(1, 3) break;
                 case 3 * 4 + 0: QEC_BWD_ACC(0, 3) break;
-                case 2 * 4 + 1: QEC_BWD_GRAD(2) if (need_chain) { QEC_BWD_ACC(1, 2) } break;
+                case 2 * 4 + 1: QEC_BWD_GRAD(2) if (need_chain) QEC_BWD_ACC(1, 2) break;
                 case 2 * 4 + 0: QEC_BWD_ACC(0, 2) break;
-                default: QEC_BWD_GRAD(1) if (need_chain) { QEC_BWD_ACC(0, 1) } break;
+                default: QEC_BWD_GRAD(1) if (need_chain) QEC_BWD_ACC(0, 1) break;
             }
 #undef QEC_BWD_GRAD
 #undef QEC_BWD_ACC
@@ -959,8 +991,8 @@ __global__ void __launch_bounds__(kPT, 2)
 template <int CL>
 static int launch_fused2_bwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
                              const float* beta, const float* poses_all, const float* stats, const float* g_pose,
-                             const float* g_agr, float* g_toqi, float* g_lrfs, float* g_act, float* g_ab, long long Nc,
-                             int K, int I, int O, int T, cudaStream_t st) {
+                             const float* g_agr, float* g_toqi, float* g_lo, float* g_lrfs, float* g_act, float* g_ab,
+                             long long Nc, int K, int I, int O, int T, cudaStream_t st) {
     const bool full = ((long long)K * I == (long long)CL * 2 * kNpMax);
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
@@ -971,14 +1003,14 @@ static int launch_fused2_bwd(const float* t_oqi, const float* lrfs, const float*
         const int rc = fused2_grid(kern, CL, fwd2_smem<CL>(), Nc, cfg, attr, cached[1]);
         if (rc) return rc;
         cfg.stream = st;
-        e = cudaLaunchKernelEx(&cfg, kern, t_oqi, lrfs, act, alpha, beta, poses_all, stats, g_pose, g_agr, g_toqi,
+        e = cudaLaunchKernelEx(&cfg, kern, t_oqi, lrfs, act, alpha, beta, poses_all, stats, g_pose, g_agr, g_toqi, g_lo,
                                g_lrfs, g_act, g_ab, Nc, K, I, O, T);
     } else {
         auto kern = routing_fused2_bwd_kernel<CL, false>;
         const int rc = fused2_grid(kern, CL, fwd2_smem<CL>(), Nc, cfg, attr, cached[0]);
         if (rc) return rc;
         cfg.stream = st;
-        e = cudaLaunchKernelEx(&cfg, kern, t_oqi, lrfs, act, alpha, beta, poses_all, stats, g_pose, g_agr, g_toqi,
+        e = cudaLaunchKernelEx(&cfg, kern, t_oqi, lrfs, act, alpha, beta, poses_all, stats, g_pose, g_agr, g_toqi, g_lo,
                                g_lrfs, g_act, g_ab, Nc, K, I, O, T);
     }
     return e == cudaSuccess ? launch_status() : (int)e;
@@ -1022,14 +1054,10 @@ extern "C" int qec_prof_read(long long* dst_host) {
 }
 #endif
 
-extern "C" int qec_routing_fused_bwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
-                                     const float* beta, const float* poses_all, const float* stats,
-                                     const float* g_pose, const float* g_agreement, float* g_toqi, float* g_lrfs,
-                                     float* g_act, float* g_alpha_beta, int BP, int K, int I, int O, int T,
-                                     void* stream) {
-    if (!qec_routing_fused_packed_supported(K, I, O, T))
-        return qec_routing_fused_bwd_scalar(t_oqi, lrfs, act, alpha, beta, poses_all, stats, g_pose, g_agreement,
-                                            g_toqi, g_lrfs, g_act, g_alpha_beta, BP, K, I, O, T, stream);
+static int fused2_bwd_entry(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
+                           const float* beta, const float* poses_all, const float* stats, const float* g_pose,
+                           const float* g_agreement, float* g_toqi, float* g_lo, float* g_lrfs, float* g_act,
+                           float* g_alpha_beta, int BP, int K, int I, int O, int T, void* stream) {
     QEC_CHECK_ARG(t_oqi, 1);
     QEC_CHECK_ARG(lrfs, 2);
     QEC_CHECK_ARG(act && alpha && beta && poses_all && stats, 3);
@@ -1040,5 +1068,31 @@ extern "C" int qec_routing_fused_bwd(const float* t_oqi, const float* lrfs, cons
     const long long Nc = (long long)BP * O;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     QEC_DISPATCH_CL(launch_fused2_bwd, t_oqi, lrfs, act, alpha, beta, poses_all, stats, g_pose, g_agreement, g_toqi,
-                    g_lrfs, g_act, g_alpha_beta, Nc, K, I, O, T, st)
+                    g_lo, g_lrfs, g_act, g_alpha_beta, Nc, K, I, O, T, st)
+}
+
+extern "C" int qec_routing_fused_bwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
+                                     const float* beta, const float* poses_all, const float* stats,
+                                     const float* g_pose, const float* g_agreement, float* g_toqi, float* g_lrfs,
+                                     float* g_act, float* g_alpha_beta, int BP, int K, int I, int O, int T,
+                                     void* stream) {
+    if (!qec_routing_fused_packed_supported(K, I, O, T))
+        return qec_routing_fused_bwd_scalar(t_oqi, lrfs, act, alpha, beta, poses_all, stats, g_pose, g_agreement,
+                                            g_toqi, g_lrfs, g_act, g_alpha_beta, BP, K, I, O, T, stream);
+    return fused2_bwd_entry(t_oqi, lrfs, act, alpha, beta, poses_all, stats, g_pose, g_agreement, g_toqi, nullptr,
+                            g_lrfs, g_act, g_alpha_beta, BP, K, I, O, T, stream);
+}
+
+// Same as qec_routing_fused_bwd, but dL/dt_oqi is delivered pre-split for tensor-core consumers:
+// g_toqi_hi = the gradient rounded to the TF32 grid, g_toqi_lo = the exact remainder (hi + lo == g).
+// Only for geometries with qec_routing_fused_packed_supported(...) == 1 (argument 15 otherwise).
+extern "C" int qec_routing_fused_bwd_split(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
+                                           const float* beta, const float* poses_all, const float* stats,
+                                           const float* g_pose, const float* g_agreement, float* g_toqi_hi,
+                                           float* g_toqi_lo, float* g_lrfs, float* g_act, float* g_alpha_beta, int BP,
+                                           int K, int I, int O, int T, void* stream) {
+    QEC_CHECK_ARG(qec_routing_fused_packed_supported(K, I, O, T), 15);
+    QEC_CHECK_ARG(g_toqi_lo, 11);
+    return fused2_bwd_entry(t_oqi, lrfs, act, alpha, beta, poses_all, stats, g_pose, g_agreement, g_toqi_hi, g_toqi_lo,
+                            g_lrfs, g_act, g_alpha_beta, BP, K, I, O, T, stream);
 }

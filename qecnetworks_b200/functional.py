@@ -128,6 +128,52 @@ class Routing(torch.autograd.Function):
         return g_votes, g_act, g_ab[0:1], g_ab[1:2], None
 
 
+def routing_fused_forward_raw(t_oqi, lrfs, activation, alpha, beta, T):
+    """no autograd: -> pose, agreement, poses_all [T,B,P,O,4], stats [B,P,O,2] (the last two are what
+    the backward needs besides the inputs)"""
+    B, P, K, I, _ = lrfs.shape
+    O = t_oqi.shape[-1] // (4 * I)
+    lrfs = _check(lrfs, "lrfs", (B, P, K, I, 4))
+    t_oqi = _check(t_oqi, "t_oqi", (B * P * K, 4 * I * O))
+    activation = _check(activation, "activation", (B, P, K * I))
+    alpha = _check(alpha, "alpha", (1,))
+    beta = _check(beta, "beta", (1,))
+    dev = lrfs.device
+    pose = torch.empty(B, P, O, 4, device=dev, dtype=torch.float32)
+    agreement = torch.empty(B, P, O, device=dev, dtype=torch.float32)
+    poses_all = torch.empty(T, B, P, O, 4, device=dev, dtype=torch.float32)
+    stats = torch.empty(B, P, O, 2, device=dev, dtype=torch.float32)
+    call("qec_routing_fused_fwd", ptr(t_oqi), ptr(lrfs), ptr(activation), ptr(alpha), ptr(beta), ptr(pose),
+         ptr(agreement), ptr(poses_all), ptr(stats), B * P, K, I, O, T, _stream())
+    return pose, agreement, poses_all, stats
+
+
+def routing_fused_backward_raw(t_oqi, lrfs, activation, alpha, beta, poses_all, stats, g_pose, g_agreement, T,
+                               need_lrfs, need_act, split=False):
+    """no autograd: -> g_toqi, g_lrfs | None, g_act | None, g_alpha_beta [2].  With split=True g_toqi is a
+    [2, B*P*K, 4*I*O] tensor: plane 0 = the gradient rounded to the TF32 grid, plane 1 = the exact remainder
+    (qec_routing_fused_bwd_split; packed-pair geometries only)."""
+    B, P, K, I, _ = lrfs.shape
+    O = t_oqi.shape[-1] // (4 * I)
+    dev = lrfs.device
+    g_pose = torch.zeros(B, P, O, 4, device=dev) if g_pose is None else g_pose.contiguous()
+    g_agreement = torch.zeros(B, P, O, device=dev) if g_agreement is None else g_agreement.contiguous()
+    g_lrfs = torch.zeros_like(lrfs) if need_lrfs else None
+    g_act = torch.zeros_like(activation) if need_act else None
+    g_ab = torch.zeros(2, device=dev, dtype=torch.float32)
+    if split:
+        g_toqi = torch.empty((2,) + tuple(t_oqi.shape), device=dev, dtype=torch.float32)
+        call("qec_routing_fused_bwd_split", ptr(t_oqi), ptr(lrfs), ptr(activation), ptr(alpha), ptr(beta),
+             ptr(poses_all), ptr(stats), ptr(g_pose), ptr(g_agreement), ptr(g_toqi[0]), ptr(g_toqi[1]), ptr(g_lrfs),
+             ptr(g_act), ptr(g_ab), B * P, K, I, O, T, _stream())
+    else:
+        g_toqi = torch.empty_like(t_oqi)
+        call("qec_routing_fused_bwd", ptr(t_oqi), ptr(lrfs), ptr(activation), ptr(alpha), ptr(beta), ptr(poses_all),
+             ptr(stats), ptr(g_pose), ptr(g_agreement), ptr(g_toqi), ptr(g_lrfs), ptr(g_act), ptr(g_ab), B * P, K, I,
+             O, T, _stream())
+    return g_toqi, g_lrfs, g_act, g_ab
+
+
 class RoutingFused(torch.autograd.Function):
     """(t_oqi [B*P*K, 4*I*O] capsule-major, lrfs [B,P,K,I,4], activation [B,P,K*I], alpha, beta, T)
     -> (pose [B,P,O,4], agreement [B,P,O]): vote generation + routing with the votes resident in
@@ -135,21 +181,8 @@ class RoutingFused(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, t_oqi, lrfs, activation, alpha, beta, num_iterations):
-        B, P, K, I, _ = lrfs.shape
-        O = t_oqi.shape[-1] // (4 * I)
-        lrfs = _check(lrfs, "lrfs", (B, P, K, I, 4))
-        t_oqi = _check(t_oqi, "t_oqi", (B * P * K, 4 * I * O))
-        activation = _check(activation, "activation", (B, P, K * I))
-        alpha = _check(alpha, "alpha", (1,))
-        beta = _check(beta, "beta", (1,))
         T = int(num_iterations)
-        dev = lrfs.device
-        pose = torch.empty(B, P, O, 4, device=dev, dtype=torch.float32)
-        agreement = torch.empty(B, P, O, device=dev, dtype=torch.float32)
-        poses_all = torch.empty(T, B, P, O, 4, device=dev, dtype=torch.float32)
-        stats = torch.empty(B, P, O, 2, device=dev, dtype=torch.float32)
-        call("qec_routing_fused_fwd", ptr(t_oqi), ptr(lrfs), ptr(activation), ptr(alpha), ptr(beta), ptr(pose),
-             ptr(agreement), ptr(poses_all), ptr(stats), B * P, K, I, O, T, _stream())
+        pose, agreement, poses_all, stats = routing_fused_forward_raw(t_oqi, lrfs, activation, alpha, beta, T)
         ctx.save_for_backward(t_oqi, lrfs, activation, alpha, beta, poses_all, stats)
         ctx.T = T
         return pose, agreement
@@ -157,20 +190,14 @@ class RoutingFused(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_pose, g_agreement):
         t_oqi, lrfs, activation, alpha, beta, poses_all, stats = ctx.saved_tensors
-        B, P, K, I, _ = lrfs.shape
-        O = t_oqi.shape[-1] // (4 * I)
-        dev = lrfs.device
-        g_pose = torch.zeros(B, P, O, 4, device=dev) if g_pose is None else g_pose.contiguous()
-        g_agreement = torch.zeros(B, P, O, device=dev) if g_agreement is None else g_agreement.contiguous()
-        need_lrfs, need_act = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
-        g_toqi = torch.empty_like(t_oqi)
-        g_lrfs = torch.zeros_like(lrfs) if need_lrfs else None
-        g_act = torch.zeros_like(activation) if need_act else None
-        g_ab = torch.zeros(2, device=dev, dtype=torch.float32)
-        call("qec_routing_fused_bwd", ptr(t_oqi), ptr(lrfs), ptr(activation), ptr(alpha), ptr(beta), ptr(poses_all),
-             ptr(stats), ptr(g_pose), ptr(g_agreement), ptr(g_toqi), ptr(g_lrfs), ptr(g_act), ptr(g_ab), B * P, K, I,
-             O, ctx.T, _stream())
+        g_toqi, g_lrfs, g_act, g_ab = routing_fused_backward_raw(
+            t_oqi, lrfs, activation, alpha, beta, poses_all, stats, g_pose, g_agreement, ctx.T,
+            ctx.needs_input_grad[1], ctx.needs_input_grad[2])
         return g_toqi, g_lrfs, g_act, g_ab[0:1], g_ab[1:2], None
+
+
+def routing_fused_packed_supported(K, I, O, T):
+    return bool(_lib.query("qec_routing_fused_packed_supported", int(K), int(I), int(O), int(T)))
 
 
 class RoutingSmall(torch.autograd.Function):

@@ -22,8 +22,8 @@ def _tf32_round(x):
     return ((x.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
-class _SplitTf32Matmul(torch.autograd.Function):
-    """y = xa @ wa^T in FP32 accuracy on the TF32 tensor cores (cuBLAS).
+def _split_tf32_matmul(xa, wa):
+    """xa @ wa^T in FP32 accuracy on the TF32 tensor cores (cuBLAS).
 
     Both operands are split x = hi + lo with hi, lo on the TF32 grid (exact inputs for the tensor
     cores) and the three significant products are ONE GEMM over a concatenated contraction axis:
@@ -31,26 +31,31 @@ class _SplitTf32Matmul(torch.autograd.Function):
     accumulated in FP32; the dropped lo*lo term and the rounding of lo are ~2^-22 relative.
     Measured on B200 for [8192,41] x [41,20480]: 122 us vs 466 us for the SIMT SGEMM (which is
     bound by its 1.4 TB/s output path, not by FLOPs), max error 9e-7 of the largest entry vs
-    3e-7 for SGEMM.  The backward stays plain FP32 SGEMM."""
+    3e-7 for SGEMM."""
+    K = xa.shape[1]
+    pad = (-3 * K) % 16  # tensor-core kernels need an aligned contraction length
+    xh = _tf32_round(xa)
+    xl = _tf32_round(xa - xh)
+    wh = _tf32_round(wa)
+    wl = _tf32_round(wa - wh)
+    A = torch.cat([xh, xh, xl, xa.new_zeros(xa.shape[0], pad)], dim=1)
+    Bm = torch.cat([wh, wl, wh, wa.new_zeros(wa.shape[0], pad)], dim=1)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        y = A @ Bm.t()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return y
+
+
+class _SplitTf32Matmul(torch.autograd.Function):
+    """y = xa @ wa^T (_split_tf32_matmul); the backward is plain FP32 SGEMM."""
 
     @staticmethod
     def forward(ctx, xa, wa):
         ctx.save_for_backward(xa, wa)
-        K = xa.shape[1]
-        pad = (-3 * K) % 16  # tensor-core kernels need an aligned contraction length
-        xh = _tf32_round(xa)
-        xl = _tf32_round(xa - xh)
-        wh = _tf32_round(wa)
-        wl = _tf32_round(wa - wh)
-        A = torch.cat([xh, xh, xl, xa.new_zeros(xa.shape[0], pad)], dim=1)
-        Bm = torch.cat([wh, wl, wh, wa.new_zeros(wa.shape[0], pad)], dim=1)
-        prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = True
-        try:
-            y = A @ Bm.t()
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = prev
-        return y
+        return _split_tf32_matmul(xa, wa)
 
     @staticmethod
     def backward(ctx, g):
@@ -60,14 +65,92 @@ class _SplitTf32Matmul(torch.autograd.Function):
         return g_xa, g_wa
 
 
-def _linear_bias_in_gemm(x, weight, bias, row_perm=None):
-    """y = [x, 1] @ [W, b]^T.  Same value as F.linear(x, W, b), but the bias rides inside the
-    GEMM (K+1) instead of a separate epilogue pass over the 671 MB output, and its gradient
-    falls out of the weight-gradient GEMM instead of a separate 671 MB reduction."""
+def _chunks(n, want=16, min_len=128):
+    """largest power of two <= want that divides n and leaves chunks of >= min_len"""
+    s = want
+    while s > 1 and (n % s or n // s < min_len):
+        s //= 2
+    return s
+
+
+def _split_tf32_grads(G2, xa, wa, need_x, need_w):
+    """g_xa = g @ wa and g_wa = g^T @ xa for g = G2[0] + G2[1] delivered pre-split by the routing
+    backward (G2[0] on the TF32 grid), on the TF32 tensor cores at FP32 accuracy:
+        g @ w = g_hi (w_hi + w_lo) + g_lo w_hi        (the lo*lo term is ~2^-22 relative)
+    The long contraction (20 480 resp. 8 192 terms) is cut into 16 chunks whose partial products are
+    summed in FP32, because the tensor-core accumulator alone loses ~5e-5 over such lengths; with the
+    chunks the error (1e-6 .. 3e-6 of the largest entry) is below that of the SIMT SGEMM it replaces
+    (3e-6 .. 6e-6) at half its time (scripts/gemm_probe7.py: 552 us vs 1 090 us for both products)."""
+    M, N = G2.shape[1], G2.shape[2]
+    K = xa.shape[1]
+    KP = K + ((-K) % 8)
+
+    def blocks(t):
+        hi = _tf32_round(t)
+        lo = _tf32_round(t - hi)
+        z = t.new_zeros(t.shape[0], KP - K)
+        return torch.cat([hi, z, lo, z], dim=1), torch.cat([hi, z], dim=1)  # [*, 2KP] for g_hi, [*, KP] for g_lo
+
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        g_xa = g_wa = None
+        if need_w:
+            S = _chunks(M)
+            X0, X1 = blocks(xa)
+            a = torch.bmm(G2[0].view(S, M // S, N).transpose(1, 2), X0.view(S, M // S, 2 * KP)).sum(0)
+            b = torch.bmm(G2[1].view(S, M // S, N).transpose(1, 2), X1.view(S, M // S, KP)).sum(0)
+            g_wa = a[:, :K] + a[:, KP:KP + K] + b[:, :K]
+        if need_x:
+            S = _chunks(N)
+            W0, W1 = blocks(wa)
+            a = torch.bmm(G2[0].view(M, S, N // S).transpose(0, 1), W0.view(S, N // S, 2 * KP)).sum(0)
+            b = torch.bmm(G2[1].view(M, S, N // S).transpose(0, 1), W1.view(S, N // S, KP)).sum(0)
+            g_xa = a[:, :K] + a[:, KP:KP + K] + b[:, :K]
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return g_xa, g_wa
+
+
+class _TransformRoutingFused(torch.autograd.Function):
+    """quater_gen2 (as xa @ wa^T, capsule-major rows) + the cluster-resident routing kernels as ONE
+    autograd node, so that the 671 MB gradient of the transforms can travel from the routing backward
+    to the two weight/input-gradient GEMMs pre-split for the tensor cores (never as a plain FP32
+    tensor): reference qec_module.py:124 + 126-147 + 172-194."""
+
+    @staticmethod
+    def forward(ctx, xa, wa, lrfs, activation, alpha, beta, num_iterations):
+        T = int(num_iterations)
+        t_oqi = _split_tf32_matmul(xa, wa)
+        pose, agreement, poses_all, stats = QF.routing_fused_forward_raw(t_oqi, lrfs, activation, alpha, beta, T)
+        ctx.save_for_backward(xa, wa, t_oqi, lrfs, activation, alpha, beta, poses_all, stats)
+        ctx.T = T
+        return pose, agreement
+
+    @staticmethod
+    def backward(ctx, g_pose, g_agreement):
+        xa, wa, t_oqi, lrfs, activation, alpha, beta, poses_all, stats = ctx.saved_tensors
+        G2, g_lrfs, g_act, g_ab = QF.routing_fused_backward_raw(
+            t_oqi, lrfs, activation, alpha, beta, poses_all, stats, g_pose, g_agreement, ctx.T,
+            ctx.needs_input_grad[2], ctx.needs_input_grad[3], split=True)
+        g_xa, g_wa = _split_tf32_grads(G2, xa, wa, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return g_xa, g_wa, g_lrfs, g_act, g_ab[0:1], g_ab[1:2], None
+
+
+def _augment(x, weight, bias, row_perm=None):
+    """([x, 1], [W, b]) so that F.linear(x, W, b) == [x, 1] @ [W, b]^T: the bias rides inside the GEMM
+    (K+1) instead of a separate epilogue pass over the 671 MB output, and its gradient falls out of the
+    weight-gradient GEMM instead of a separate 671 MB reduction"""
     xa = torch.cat([x, x.new_ones(x.shape[0], 1)], dim=1)
     wa = torch.cat([weight, bias.unsqueeze(1)], dim=1)
     if row_perm is not None:
         wa = wa.index_select(0, row_perm)  # output features re-ordered for free inside the GEMM
+    return xa, wa
+
+
+def _linear_bias_in_gemm(x, weight, bias, row_perm=None):
+    """y = [x, 1] @ [W, b]^T == F.linear(x, W, b) on the tensor cores at FP32 accuracy"""
+    xa, wa = _augment(x, weight, bias, row_perm)
     return _SplitTf32Matmul.apply(xa, wa)
 
 
@@ -120,8 +203,15 @@ class QecModule(Module):
         h = self.quater_gen1(xrot.view(B * P * K, 3 * I))
         if K * I >= self.FUSED_MIN_VOTES and QF.routing_fused_supported(K, I, O, self.num_iterations):
             # capsule-major transforms straight out of the GEMM; votes never touch HBM
-            t_oqi = _linear_bias_in_gemm(h, self.quater_gen2.weight, self.quater_gen2.bias, self._oqi_perm(I, O))
-            pose, agreement = QF.routing_fused(t_oqi, lrfs, act_flat, self.alpha, self.beta, self.num_iterations)
+            if QF.routing_fused_packed_supported(K, I, O, self.num_iterations):
+                xa, wa = _augment(h, self.quater_gen2.weight, self.quater_gen2.bias, self._oqi_perm(I, O))
+                pose, agreement = _TransformRoutingFused.apply(xa, wa, lrfs, act_flat, self.alpha, self.beta,
+                                                               self.num_iterations)
+            else:
+                t_oqi = _linear_bias_in_gemm(h, self.quater_gen2.weight, self.quater_gen2.bias,
+                                             self._oqi_perm(I, O))
+                pose, agreement = QF.routing_fused(t_oqi, lrfs, act_flat, self.alpha, self.beta,
+                                                   self.num_iterations)
         else:
             t_raw = _linear_bias_in_gemm(h, self.quater_gen2.weight, self.quater_gen2.bias)
             votes = QF.votes(lrfs, t_raw)

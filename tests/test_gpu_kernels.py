@@ -342,6 +342,101 @@ def test_routing_fused(B, P, K, I, O, T):
     assert max_err(agr.detach().cpu(), agr2.detach().cpu()) < 1e-5
 
 
+@pytest.mark.parametrize("B,P,K,I,O,T", [(2, 1, 256, 128, 3, 3), (1, 2, 100, 30, 3, 3), (2, 1, 37, 6, 5, 1), (1, 1, 1, 2, 1, 3)])
+def test_routing_fused_packed_vs_scalar_and_split(B, P, K, I, O, T):
+    """the packed-pair kernels (routing_fused2.cu) against the scalar ones (routing_fused.cu) through the
+    C ABI on the same inputs, incl. a capsule with a single live vote (|<pose, vote>| = 1: the distance
+    gradient is infinite there and must be selected away, not multiplied by zero); and the pre-split
+    gradient of qec_routing_fused_bwd_split: hi on the TF32 grid, hi + lo == g bit-exactly"""
+    from qecnetworks_b200 import functional as QF, _lib
+
+    dev = cuda()
+    assert QF.routing_fused_packed_supported(K, I, O, T)
+    gen = torch.Generator().manual_seed(K * 3 + I)
+    J = K * I
+    lrfs = clustered((B, P, K, I), gen, spread=0.3)
+    act = (torch.rand(B, P, J, generator=gen) * 0.6 + 0.3) * (torch.rand(B, P, J, generator=gen) < 0.85)
+    act[:, :, 0] = 1.0
+    if J == 2:
+        act[:, :, 1] = 0.0
+    lrfs = (lrfs * (act.view(B, P, K, I, 1) != 0)).to(dev)
+    act = act.to(dev)
+    base = torch.randn(1, O, 4, 1, generator=gen)
+    t = (base + 0.25 * torch.randn(B * P * K, O, 4, I, generator=gen)).reshape(B * P * K, 4 * I * O).to(dev)
+    alpha, beta = torch.tensor([1.2], device=dev), torch.tensor([0.8], device=dev)
+    Gp = torch.randn(B, P, O, 4, generator=gen).to(dev)
+    Ga = torch.randn(B, P, O, generator=gen).to(dev)
+    st = torch.cuda.current_stream().cuda_stream
+    Nc = B * P * O
+
+    def fwd(name):
+        pose = torch.empty(Nc, 4, device=dev); agr = torch.empty(Nc, device=dev)
+        pa = torch.empty(T, Nc, 4, device=dev); stt = torch.empty(Nc, 2, device=dev)
+        _lib.call(name, t.data_ptr(), lrfs.data_ptr(), act.data_ptr(), alpha.data_ptr(), beta.data_ptr(),
+                  pose.data_ptr(), agr.data_ptr(), pa.data_ptr(), stt.data_ptr(), B * P, K, I, O, T, st)
+        return pose, agr, pa, stt
+
+    def bwd(name, f, split=False):
+        g_t = torch.full((2 if split else 1,) + tuple(t.shape), 7.0, device=dev)
+        g_l = torch.zeros_like(lrfs); g_a = torch.zeros_like(act); g_ab = torch.zeros(2, device=dev)
+        outs = [g_t[0].data_ptr()] + ([g_t[1].data_ptr()] if split else [])
+        _lib.call(name, t.data_ptr(), lrfs.data_ptr(), act.data_ptr(), alpha.data_ptr(), beta.data_ptr(),
+                  f[2].data_ptr(), f[3].data_ptr(), Gp.data_ptr(), Ga.data_ptr(), *outs, g_l.data_ptr(),
+                  g_a.data_ptr(), g_ab.data_ptr(), B * P, K, I, O, T, st)
+        torch.cuda.synchronize()
+        return g_t, g_l, g_a, g_ab
+
+    fp, fs = fwd("qec_routing_fused_fwd"), fwd("qec_routing_fused_fwd_scalar")
+    assert quat_err(fp[0].cpu(), fs[0].cpu()) < 2e-6 and max_err(fp[1].cpu(), fs[1].cpu()) < 2e-6
+    assert quat_err(fp[2].cpu(), fs[2].cpu()) < 2e-6 and max_err(fp[3].cpu(), fs[3].cpu()) < 1e-5
+    bp, bs = bwd("qec_routing_fused_bwd", fs), bwd("qec_routing_fused_bwd_scalar", fs)
+    for k, (x, y) in enumerate(zip(bp, bs)):
+        assert torch.isfinite(x).all(), k
+        # dL/dlrfs keeps the radial component the normalisation projects out of dL/dt: it inherits the
+        # 1/gap conditioning of the adjoint solve, so the two summation orders differ by ~1e-4 there
+        assert rel_err(x.cpu(), y.cpu()) < (5e-4 if k == 1 else 2e-5), (k, rel_err(x.cpu(), y.cpu()))
+    sp = bwd("qec_routing_fused_bwd_split", fs, split=True)
+    hi, lo = sp[0][0], sp[0][1]
+    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0          # hi is on the TF32 grid
+    assert torch.equal(hi + lo, bp[0][0])                                  # exact split of the same gradient
+    assert float(lo.abs().max()) <= float(bp[0][0].abs().max()) * 2.0 ** -11
+
+
+def test_transform_routing_node_matches_plain_path():
+    """_TransformRoutingFused (tensor-core backward GEMMs fed by the pre-split gradient) against the plain
+    path (FP32 SGEMM backward) on a pool2-shaped layer: same outputs, same gradients"""
+    from qecnetworks_b200 import functional as QF
+    from qecnetworks_b200 import qec_module as QM
+
+    dev = cuda()
+    B, P, K, I, O, T = 2, 1, 256, 128, 5, 3
+    gen = torch.Generator().manual_seed(5)
+    lrfs = clustered((B, P, K, I), gen, spread=0.3).to(dev)
+    act = (torch.rand(B, P, K * I, generator=gen) * 0.6 + 0.3).to(dev)
+    h = torch.randn(B * P * K, O, generator=gen).to(dev)
+    W = (0.3 * torch.randn(4 * I * O, O, generator=gen)).to(dev)
+    b = (0.3 * torch.randn(4 * I * O, generator=gen)).to(dev)
+    alpha, beta = torch.tensor([1.1], device=dev), torch.tensor([0.9], device=dev)
+    Gp = torch.randn(B, P, O, 4, generator=gen).to(dev)
+    Ga = torch.randn(B, P, O, generator=gen).to(dev)
+
+    def run(node):
+        hh, WW, bb = (x.clone().requires_grad_(True) for x in (h, W, b))
+        ll, aa = lrfs.clone().requires_grad_(True), act.clone().requires_grad_(True)
+        xa, wa = QM._augment(hh, WW, bb)
+        if node:
+            pose, agr = QM._TransformRoutingFused.apply(xa, wa, ll, aa, alpha, beta, T)
+        else:
+            pose, agr = QF.routing_fused(QM._SplitTf32Matmul.apply(xa, wa), ll, aa, alpha, beta, T)
+        ((pose * Gp).sum() + (agr * Ga).sum()).backward()
+        return pose.detach(), agr.detach(), hh.grad, WW.grad, bb.grad, ll.grad, aa.grad
+
+    a, c = run(True), run(False)
+    assert quat_err(a[0].cpu(), c[0].cpu()) < 1e-6 and max_err(a[1].cpu(), c[1].cpu()) < 1e-6
+    for k in range(2, 7):
+        assert rel_err(a[k].cpu(), c[k].cpu()) < (5e-4 if k == 5 else 2e-5), (k, rel_err(a[k].cpu(), c[k].cpu()))
+
+
 # ---------------------------------------------------------------- register-resident pool1 kernel
 @pytest.mark.parametrize("B,P,K,O,T", [(2, 8, 9, 16, 3), (1, 5, 9, 130, 3), (2, 3, 4, 7, 1), (1, 4, 13, 40, 2), (1, 2, 16, 33, 5)])
 def test_routing_small(B, P, K, O, T):
