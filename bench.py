@@ -164,13 +164,15 @@ def kernel_work(name, dims, T):
         if name == "qec_votes_fwd":
             return 32 * Nv + 16 * Nn, 48 * Nv
         return 48 * Nv + 32 * Nn, 2 * 48 * Nv
-    if name in ("qec_routing_fused_fwd", "qec_routing_fused_bwd"):
+    if name in ("qec_routing_fused_fwd", "qec_routing_fused_bwd", "qec_routing_fused_bwd_split"):
         # votes generated on chip from the transforms: t read once (fwd) + its gradient written once (bwd)
         BP, K, I, O, T = dims[:5]
         Nv, Nc, Nn = BP * K * I * O, BP * O, BP * K * I
         if name == "qec_routing_fused_fwd":
             return 16 * Nv + 20 * Nn + 20 * Nc, (48 + 49 * T) * Nv + 2000 * T * Nc + 20 * Nc
-        return 32 * Nv + 40 * Nn + 20 * Nc, (2 * 48 + 2 * 49 * T) * Nv + 300 * T * Nc
+        # _split writes the transform gradient as two FP32 planes (TF32 hi + remainder) for the tensor-core GEMMs
+        extra = 16 * Nv if name.endswith("_split") else 0
+        return 32 * Nv + extra + 40 * Nn + 20 * Nc, (2 * 48 + 2 * 49 * T) * Nv + 300 * T * Nc
     if name in ("qec_routing_small_fwd", "qec_routing_small_bwd"):
         # I = 1, composed transform (24 FLOP / vote) evaluated in-kernel: no transform tensor at all
         BP, K, O, T = dims[:4]
@@ -199,6 +201,18 @@ def measure_fp32_peak(torch, _lib, dev):
         torch.cuda.synchronize()
         best = max(best, flop / (e0.elapsed_time(e1) * 1e-3) / 1e12)
     return best
+
+
+def load_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full
+    capture of the same workload (profiles/ncu_traffic.json, written from the .ncu-rep by
+    scripts/ncu_traffic.py); None if there is no capture for it"""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        rec = json.load(open(path)).get(kernel)
+        return None if rec is None else float(rec["dram_bytes"])
+    except (OSError, ValueError, KeyError):
+        return None
 
 
 def load_peaks():
@@ -366,11 +380,13 @@ def run_b200(a):
             fp_time = top["alg_flop"] / (fp32_peak * 1e12)
             if hbm_time >= fp_time:
                 roofline = {"kernel": top["kernel"], "dims": top["dims"], "bound": "hbm", "achieved": top["hbm_gbs"],
-                            "peak": hbm_peak, "unit": "GB/s", "frac": top["hbm_frac"], "traffic": None,
+                            "peak": hbm_peak, "unit": "GB/s", "frac": top["hbm_frac"], "traffic": load_traffic(top["kernel"]),
                             "peak_source": peak_src, "ms": top["ms"]}
             else:
                 roofline = {"kernel": top["kernel"], "dims": top["dims"], "bound": "fp32", "achieved": top["fp32_tflops"],
-                            "peak": fp32_peak, "unit": "TFLOP/s", "frac": top["fp32_frac"], "traffic": None,
+                            "peak": fp32_peak, "unit": "TFLOP/s", "frac": top["fp32_frac"],
+                            "traffic": load_traffic(top["kernel"]), "alg_bytes": top["alg_bytes"],
+                            "hbm_frac": top["hbm_frac"],
                             "peak_source": "FFMA microbenchmark in this run (qec_ffma_peak)", "ms": top["ms"],
                             "note": "FP32-FMA-bound by design (4x4 quaternion algebra is not a dense contraction); "
                                     "schema extension of hbm|tensor"}

@@ -100,6 +100,9 @@ __device__ __forceinline__ f2 ldg_f2(const float* p) {
 //      (bcast) is the second and last CTA barrier of a sweep.
 // Compared with barrier.cluster + DSMEM loads (ClusterReducer) this removes the cluster-scope
 // MEMBAR, one DSMEM round trip and two CTA barriers from the serial path of every sweep.
+// (Pushing the 64 WARP partials of a cluster directly -- no CTA barrier, no scratch -- was measured
+// too: 8x the remote stores make the wait for the totals longer than the barrier it saves,
+// forward 0.51 -> 0.64 ms.)
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
@@ -865,6 +868,9 @@ __global__ void __launch_bounds__(kPT, 2)
     const unsigned trow = 4u * I * O;
     const bool need_chain = g_act != nullptr;
     float ga_tot = 0.f, gb_tot = 0.f;
+#ifdef QEC_PROF
+    int prof_n = 0;
+#endif
 
     Bwd2Geom B;
     B.act = act; B.lrfs = lrfs; B.t_oqi = t_oqi; B.g_toqi = g_toqi; B.g_lo = g_lo; B.g_lrfs = g_lrfs; B.g_act = g_act;
@@ -926,6 +932,7 @@ __global__ void __launch_bounds__(kPT, 2)
         };
 
         float acc[15];
+        QEC_EVT(0);
         {
             const Bwd2Caps C = caps(0, kTB);
             if (T == 3) bwd2_sweep0<3, FULL>(np, B, C, sA, sB, acc);
@@ -936,7 +943,12 @@ __global__ void __launch_bounds__(kPT, 2)
         const int nsweeps = need_chain ? T : 1;
         for (int k = 1; k <= nsweeps; ++k) {
             const int t = T - k;  // level being completed
+            QEC_EVT(7 * (k - 1) + 1);
+#ifdef QEC_PROF
+            red.reduce(acc, 7 * (k - 1) + 2, prof_n);
+#else
             red.reduce(acc);      // sums of the level accumulated by the previous sweep
+#endif
             if (red.solver()) {
                 const Quat p = ldq_nc(poses_all + ((size_t)t * Nc + c) * 4);
                 const float rs = 1.f / fmaxf(acc[14], 1e-12f);
@@ -951,7 +963,9 @@ __global__ void __launch_bounds__(kPT, 2)
                     capsS[t * 8 + 4] = rs;
                 }
             }
+            QEC_EVT(7 * (k - 1) + 5);
             red.sync();  // u^t, 1/S^t visible to the CTA; the reducer's scratch may be reused
+            QEC_EVT(7 * (k - 1) + 6);
             // the votes die with the last pass over them: that pass refills the slots for the next capsule
             const bool pf_grad = more && !need_chain;
             const bool pf_acc = more && (k == nsweeps);
@@ -960,6 +974,7 @@ __global__ void __launch_bounds__(kPT, 2)
         const Bwd2Caps C = caps(T_ - 1, T_ - 1);                                               \
         if (pf_grad) bwd2_grad_pass<T_, FULL, true>(np, B, C, w0, sA, sB, offT_next);          \
         else bwd2_grad_pass<T_, FULL, false>(np, B, C, w0, sA, sB, offT_next);                 \
+        QEC_EVT(7);                                                                            \
     }
 #define QEC_BWD_ACC(TT_, T_)                                                                   \
     {                                                                                          \
@@ -978,6 +993,8 @@ __global__ void __launch_bounds__(kPT, 2)
 #undef QEC_BWD_GRAD
 #undef QEC_BWD_ACC
         }
+        QEC_EVT(22);
+        QEC_EVT_NEXT();
         // the next capsule's sweep 0 touches this thread's own slots only; the reducer's scratch is
         // protected by the barriers inside reduce() / bcast()
     }
