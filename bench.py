@@ -170,8 +170,8 @@ def kernel_work(name, dims, T):
         Nv, Nc, Nn = BP * K * I * O, BP * O, BP * K * I
         if name == "qec_routing_fused_fwd":
             return 16 * Nv + 20 * Nn + 20 * Nc, (48 + 49 * T) * Nv + 2000 * T * Nc + 20 * Nc
-        # _split writes the transform gradient as two FP32 planes (TF32 hi + remainder) for the tensor-core GEMMs
-        extra = 16 * Nv if name.endswith("_split") else 0
+        # _split writes the transform gradient as TF32 hi (4 B) + BF16 remainder (2 B) for the tensor-core GEMMs
+        extra = 8 * Nv if name.endswith("_split") else 0
         return 32 * Nv + extra + 40 * Nn + 20 * Nc, (2 * 48 + 2 * 49 * T) * Nv + 300 * T * Nc
     if name in ("qec_routing_small_fwd", "qec_routing_small_bwd"):
         # I = 1, composed transform (24 FLOP / vote) evaluated in-kernel: no transform tensor at all
@@ -444,6 +444,12 @@ def run_b200(a):
 
 def main():
     a = parse_args()
+    # stdout carries exactly ONE JSON line: anything libraries print there while the run is in flight
+    # (e.g. "NCCL version ..." at communicator creation) is routed to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -147,13 +147,13 @@ int qec_routing_fused_bwd_scalar(const float* t_oqi, const float* lrfs, const fl
                                  float* g_alpha_beta, int BP, int K, int I, int O, int T, void* stream);
 
 /* qec_routing_fused_bwd with dL/dt_oqi delivered pre-split for tensor-core consumers (the backward
- * GEMMs of quater_gen2 at FP32 accuracy): g_toqi_hi = the gradient rounded to the TF32 grid,
- * g_toqi_lo = the exact remainder (hi + lo == g bit-exactly).  Only where
+ * GEMMs of quater_gen2 at FP32 accuracy): g_toqi_hi = the gradient rounded to the TF32 grid (FP32
+ * storage), g_toqi_lo = the remainder g - hi as BF16 (same shape; |g - hi - lo| <= 2^-20 |g|).  Only where
  * qec_routing_fused_packed_supported(...) == 1; returns -15 otherwise.  No reference counterpart
  * (the reference's backward of nn.Linear is an FP32 cuBLAS SGEMM, models/qec_module.py:124). */
 int qec_routing_fused_bwd_split(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
                                 const float* beta, const float* poses_all, const float* stats, const float* g_pose,
-                                const float* g_agreement, float* g_toqi_hi, float* g_toqi_lo, float* g_lrfs,
+                                const float* g_agreement, float* g_toqi_hi, unsigned short* g_toqi_lo, float* g_lrfs,
                                 float* g_act, float* g_alpha_beta, int BP, int K, int I, int O, int T, void* stream);
 
 /* FP32 FMA roof: blocks*256 threads x iters x 16 dependent-chain FMAs

@@ -214,6 +214,13 @@ __device__ __forceinline__ f2 tf32_round2(f2 v) {
     return pk(__uint_as_float(a), __uint_as_float(b));
 }
 
+// (lo, hi) -> two BF16 (round to nearest even) in one word, lo at the lower address
+__device__ __forceinline__ unsigned bf16x2(f2 v) {
+    unsigned d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi(v)), "f"(lo(v)));
+    return d;
+}
+
 // two votes at once (reference models/qec_module.py:129-145, scalar twin: make_vote in vote_math.cuh)
 struct VotePair {
     Quat2 vote;
@@ -631,7 +638,7 @@ struct Bwd2Geom {
     const float* lrfs;
     const float* t_oqi;
     float* g_toqi;
-    float* g_lo;     // nullable: if set, g_toqi receives the TF32-rounded gradient and g_lo the remainder
+    unsigned short* g_lo;  // nullable (bf16): if set, g_toqi receives the TF32-rounded gradient, g_lo the remainder
     float* g_lrfs;   // nullable
     float* g_act;    // nullable: no activation gradient -> only the top level is processed
     unsigned offA;   // bp * J + j_begin: first vote of this CTA's slice in act / g_act (x4 in lrfs / g_lrfs)
@@ -706,15 +713,15 @@ __device__ __forceinline__ void bwd2_grad_pass(int np, const Bwd2Geom& B, const 
             float* gp = B.g_toqi + (size_t)(B.offT + (unsigned)w.off);
             if (B.g_lo != nullptr) {
                 // pre-split for the tensor-core GEMMs that consume it (quater_gen2's backward at FP32
-                // accuracy): hi on the TF32 grid (an exact tensor-core input), lo = g - hi exactly
-                float* gq2 = B.g_lo + (size_t)(B.offT + (unsigned)w.off);
+                // accuracy): hi on the TF32 grid (an exact tensor-core input); the remainder g - hi (exact in
+                // FP32, at most 2^-11 |g|) only has to carry ~11 more bits and travels as BF16
+                unsigned* gq2 = reinterpret_cast<unsigned*>(B.g_lo + (size_t)(B.offT + (unsigned)w.off));
                 const f2 hw = tf32_round2(gt.w), hx = tf32_round2(gt.x), hy = tf32_round2(gt.y), hz = tf32_round2(gt.z);
-                const f2 lw = fma2(hw, bc(-1.f), gt.w), lx = fma2(hx, bc(-1.f), gt.x), ly = fma2(hy, bc(-1.f), gt.y),
-                         lz = fma2(hz, bc(-1.f), gt.z);
-                *reinterpret_cast<float2*>(gq2) = make_float2(lo(lw), hi(lw));
-                *reinterpret_cast<float2*>(gq2 + B.I) = make_float2(lo(lx), hi(lx));
-                *reinterpret_cast<float2*>(gq2 + 2 * B.I) = make_float2(lo(ly), hi(ly));
-                *reinterpret_cast<float2*>(gq2 + 3 * B.I) = make_float2(lo(lz), hi(lz));
+                const int Ih = B.I >> 1;  // pair stride in 32-bit words
+                gq2[0] = bf16x2(fma2(hw, bc(-1.f), gt.w));
+                gq2[Ih] = bf16x2(fma2(hx, bc(-1.f), gt.x));
+                gq2[2 * Ih] = bf16x2(fma2(hy, bc(-1.f), gt.y));
+                gq2[3 * Ih] = bf16x2(fma2(hz, bc(-1.f), gt.z));
                 gt.w = hw; gt.x = hx; gt.y = hy; gt.z = hz;
             }
             *reinterpret_cast<float2*>(gp) = make_float2(lo(gt.w), hi(gt.w));
@@ -848,7 +855,7 @@ __global__ void __launch_bounds__(kPT, 2)
                               const float* __restrict__ act, const float* __restrict__ alpha_p,
                               const float* __restrict__ beta_p, const float* __restrict__ poses_all,
                               const float* __restrict__ stats, const float* __restrict__ g_pose,
-                              const float* __restrict__ g_agr, float* __restrict__ g_toqi, float* g_lo, float* g_lrfs,
+                              const float* __restrict__ g_agr, float* __restrict__ g_toqi, unsigned short* g_lo, float* g_lrfs,
                               float* g_act, float* g_alpha_beta, long long Nc, int K, int I, int O, int T) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* __restrict__ sA = reinterpret_cast<float4*>(smem_raw);
@@ -1008,7 +1015,8 @@ __global__ void __launch_bounds__(kPT, 2)
 template <int CL>
 static int launch_fused2_bwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
                              const float* beta, const float* poses_all, const float* stats, const float* g_pose,
-                             const float* g_agr, float* g_toqi, float* g_lo, float* g_lrfs, float* g_act, float* g_ab,
+                             const float* g_agr, float* g_toqi, unsigned short* g_lo, float* g_lrfs, float* g_act,
+                             float* g_ab,
                              long long Nc, int K, int I, int O, int T, cudaStream_t st) {
     const bool full = ((long long)K * I == (long long)CL * 2 * kNpMax);
     cudaLaunchConfig_t cfg = {};
@@ -1073,7 +1081,7 @@ extern "C" int qec_prof_read(long long* dst_host) {
 
 static int fused2_bwd_entry(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
                            const float* beta, const float* poses_all, const float* stats, const float* g_pose,
-                           const float* g_agreement, float* g_toqi, float* g_lo, float* g_lrfs, float* g_act,
+                           const float* g_agreement, float* g_toqi, unsigned short* g_lo, float* g_lrfs, float* g_act,
                            float* g_alpha_beta, int BP, int K, int I, int O, int T, void* stream) {
     QEC_CHECK_ARG(t_oqi, 1);
     QEC_CHECK_ARG(lrfs, 2);
@@ -1101,12 +1109,13 @@ extern "C" int qec_routing_fused_bwd(const float* t_oqi, const float* lrfs, cons
 }
 
 // Same as qec_routing_fused_bwd, but dL/dt_oqi is delivered pre-split for tensor-core consumers:
-// g_toqi_hi = the gradient rounded to the TF32 grid, g_toqi_lo = the exact remainder (hi + lo == g).
+// g_toqi_hi = the gradient rounded to the TF32 grid (FP32 storage), g_toqi_lo = the remainder g - hi
+// rounded to BF16 (|g - hi - lo| <= 2^-20 |g|).
 // Only for geometries with qec_routing_fused_packed_supported(...) == 1 (argument 15 otherwise).
 extern "C" int qec_routing_fused_bwd_split(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
                                            const float* beta, const float* poses_all, const float* stats,
                                            const float* g_pose, const float* g_agreement, float* g_toqi_hi,
-                                           float* g_toqi_lo, float* g_lrfs, float* g_act, float* g_alpha_beta, int BP,
+                                           unsigned short* g_toqi_lo, float* g_lrfs, float* g_act, float* g_alpha_beta, int BP,
                                            int K, int I, int O, int T, void* stream) {
     QEC_CHECK_ARG(qec_routing_fused_packed_supported(K, I, O, T), 15);
     QEC_CHECK_ARG(g_toqi_lo, 11);

@@ -151,8 +151,8 @@ def routing_fused_forward_raw(t_oqi, lrfs, activation, alpha, beta, T):
 def routing_fused_backward_raw(t_oqi, lrfs, activation, alpha, beta, poses_all, stats, g_pose, g_agreement, T,
                                need_lrfs, need_act, split=False):
     """no autograd: -> g_toqi, g_lrfs | None, g_act | None, g_alpha_beta [2].  With split=True g_toqi is a
-    [2, B*P*K, 4*I*O] tensor: plane 0 = the gradient rounded to the TF32 grid, plane 1 = the exact remainder
-    (qec_routing_fused_bwd_split; packed-pair geometries only)."""
+    pair (hi, lo) of [B*P*K, 4*I*O] tensors: hi (float32) = the gradient rounded to the TF32 grid, lo
+    (bfloat16) = the remainder (qec_routing_fused_bwd_split; packed-pair geometries only)."""
     B, P, K, I, _ = lrfs.shape
     O = t_oqi.shape[-1] // (4 * I)
     dev = lrfs.device
@@ -162,7 +162,7 @@ def routing_fused_backward_raw(t_oqi, lrfs, activation, alpha, beta, poses_all, 
     g_act = torch.zeros_like(activation) if need_act else None
     g_ab = torch.zeros(2, device=dev, dtype=torch.float32)
     if split:
-        g_toqi = torch.empty((2,) + tuple(t_oqi.shape), device=dev, dtype=torch.float32)
+        g_toqi = (torch.empty_like(t_oqi), torch.empty(t_oqi.shape, device=dev, dtype=torch.bfloat16))
         call("qec_routing_fused_bwd_split", ptr(t_oqi), ptr(lrfs), ptr(activation), ptr(alpha), ptr(beta),
              ptr(poses_all), ptr(stats), ptr(g_pose), ptr(g_agreement), ptr(g_toqi[0]), ptr(g_toqi[1]), ptr(g_lrfs),
              ptr(g_act), ptr(g_ab), B * P, K, I, O, T, _stream())

@@ -65,23 +65,24 @@ class _SplitTf32Matmul(torch.autograd.Function):
         return g_xa, g_wa
 
 
-def _chunks(n, want=16, min_len=128):
-    """largest power of two <= want that divides n and leaves chunks of >= min_len"""
-    s = want
-    while s > 1 and (n % s or n // s < min_len):
-        s //= 2
+def _chunks(n, length=1024):
+    """number of chunks (a power of two dividing n) that makes them about `length` long"""
+    s = 1
+    while n % (2 * s) == 0 and n // (2 * s) >= length:
+        s *= 2
     return s
 
 
-def _split_tf32_grads(G2, xa, wa, need_x, need_w):
-    """g_xa = g @ wa and g_wa = g^T @ xa for g = G2[0] + G2[1] delivered pre-split by the routing
-    backward (G2[0] on the TF32 grid), on the TF32 tensor cores at FP32 accuracy:
+def _split_tf32_grads(g_hi, g_lo, xa, wa, need_x, need_w):
+    """g_xa = g @ wa and g_wa = g^T @ xa for g = g_hi + g_lo delivered pre-split by the routing backward
+    (g_hi float32 on the TF32 grid, g_lo the remainder in bfloat16), on the tensor cores at FP32 accuracy:
         g @ w = g_hi (w_hi + w_lo) + g_lo w_hi        (the lo*lo term is ~2^-22 relative)
-    The long contraction (20 480 resp. 8 192 terms) is cut into 16 chunks whose partial products are
-    summed in FP32, because the tensor-core accumulator alone loses ~5e-5 over such lengths; with the
-    chunks the error (1e-6 .. 3e-6 of the largest entry) is below that of the SIMT SGEMM it replaces
-    (3e-6 .. 6e-6) at half its time (scripts/gemm_probe7.py: 552 us vs 1 090 us for both products)."""
-    M, N = G2.shape[1], G2.shape[2]
+    with the first product a TF32 GEMM over [w_hi | w_lo] and the second a BF16 GEMM.  The long
+    contraction (20 480 resp. 8 192 terms) is cut into chunks of ~1 000 whose partial products are summed
+    in FP32, because the tensor-core accumulator alone loses ~5e-5 over such lengths; with the chunks the
+    error (1e-6 .. 6e-6 of the largest entry) is that of the SIMT SGEMM it replaces (3e-6 .. 6e-6) at
+    40 % of its time (scripts/gemm_probe7.py: 430 us vs 1 090 us for both products)."""
+    M, N = g_hi.shape
     K = xa.shape[1]
     KP = K + ((-K) % 8)
 
@@ -89,7 +90,7 @@ def _split_tf32_grads(G2, xa, wa, need_x, need_w):
         hi = _tf32_round(t)
         lo = _tf32_round(t - hi)
         z = t.new_zeros(t.shape[0], KP - K)
-        return torch.cat([hi, z, lo, z], dim=1), torch.cat([hi, z], dim=1)  # [*, 2KP] for g_hi, [*, KP] for g_lo
+        return torch.cat([hi, z, lo, z], dim=1), torch.cat([hi, z], dim=1).to(torch.bfloat16)
 
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
@@ -98,14 +99,16 @@ def _split_tf32_grads(G2, xa, wa, need_x, need_w):
         if need_w:
             S = _chunks(M)
             X0, X1 = blocks(xa)
-            a = torch.bmm(G2[0].view(S, M // S, N).transpose(1, 2), X0.view(S, M // S, 2 * KP)).sum(0)
-            b = torch.bmm(G2[1].view(S, M // S, N).transpose(1, 2), X1.view(S, M // S, KP)).sum(0)
+            a = torch.bmm(g_hi.view(S, M // S, N).transpose(1, 2), X0.view(S, M // S, 2 * KP)).sum(0)
+            b = torch.bmm(g_lo.view(S, M // S, N).transpose(1, 2), X1.view(S, M // S, KP),
+                          out_dtype=torch.float32).sum(0)
             g_wa = a[:, :K] + a[:, KP:KP + K] + b[:, :K]
         if need_x:
             S = _chunks(N)
             W0, W1 = blocks(wa)
-            a = torch.bmm(G2[0].view(M, S, N // S).transpose(0, 1), W0.view(S, N // S, 2 * KP)).sum(0)
-            b = torch.bmm(G2[1].view(M, S, N // S).transpose(0, 1), W1.view(S, N // S, KP)).sum(0)
+            a = torch.bmm(g_hi.view(M, S, N // S).transpose(0, 1), W0.view(S, N // S, 2 * KP)).sum(0)
+            b = torch.bmm(g_lo.view(M, S, N // S).transpose(0, 1), W1.view(S, N // S, KP),
+                          out_dtype=torch.float32).sum(0)
             g_xa = a[:, :K] + a[:, KP:KP + K] + b[:, :K]
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
@@ -130,10 +133,10 @@ class _TransformRoutingFused(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_pose, g_agreement):
         xa, wa, t_oqi, lrfs, activation, alpha, beta, poses_all, stats = ctx.saved_tensors
-        G2, g_lrfs, g_act, g_ab = QF.routing_fused_backward_raw(
+        (g_hi, g_lo), g_lrfs, g_act, g_ab = QF.routing_fused_backward_raw(
             t_oqi, lrfs, activation, alpha, beta, poses_all, stats, g_pose, g_agreement, ctx.T,
             ctx.needs_input_grad[2], ctx.needs_input_grad[3], split=True)
-        g_xa, g_wa = _split_tf32_grads(G2, xa, wa, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        g_xa, g_wa = _split_tf32_grads(g_hi, g_lo, xa, wa, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return g_xa, g_wa, g_lrfs, g_act, g_ab[0:1], g_ab[1:2], None
 
 

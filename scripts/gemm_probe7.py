@@ -42,3 +42,20 @@ for S in (1, 4, 16, 32, 64):
     print("S %2d  g_w %.0f us err %.2e | g_x %.0f us err %.2e" % (
         S, timeit(gw), float((gw() - refw).abs().max() / refw.abs().max()),
         timeit(gx), float((gx() - refx).abs().max() / refx.abs().max())))
+
+# variant: the remainder plane in BF16 (it only has to carry ~11 bits below the TF32 plane)
+Glo = (gt - G2[0]).to(torch.bfloat16)
+X1b = X1.to(torch.bfloat16); W1b = W1.to(torch.bfloat16)
+for S in (8, 16):
+    R, C = M // S, N // S
+    def gw():
+        a = torch.bmm(G2[0].view(S, R, N).transpose(1, 2), X0.view(S, R, 2 * KP)).sum(0)
+        b = torch.bmm(Glo.view(S, R, N).transpose(1, 2), X1b.view(S, R, KP), out_dtype=torch.float32).sum(0)
+        return a[:, :K] + a[:, KP:KP + K] + b[:, :K]
+    def gx():
+        a = torch.bmm(G2[0].view(M, S, C).transpose(0, 1), W0.view(S, C, 2 * KP)).sum(0)
+        b = torch.bmm(Glo.view(M, S, C).transpose(0, 1), W1b.view(S, C, KP), out_dtype=torch.float32).sum(0)
+        return a[:, :K] + a[:, KP:KP + K] + b[:, :K]
+    print("bf16-lo S %2d  g_w %.0f us err %.2e | g_x %.0f us err %.2e" % (
+        S, timeit(gw), float((gw() - refw).abs().max() / refw.abs().max()),
+        timeit(gx), float((gx() - refx).abs().max() / refx.abs().max())))

@@ -377,9 +377,11 @@ def test_routing_fused_packed_vs_scalar_and_split(B, P, K, I, O, T):
         return pose, agr, pa, stt
 
     def bwd(name, f, split=False):
-        g_t = torch.full((2 if split else 1,) + tuple(t.shape), 7.0, device=dev)
+        g_t = [torch.full(tuple(t.shape), 7.0, device=dev)]
+        if split:
+            g_t.append(torch.full(tuple(t.shape), 7.0, device=dev, dtype=torch.bfloat16))
         g_l = torch.zeros_like(lrfs); g_a = torch.zeros_like(act); g_ab = torch.zeros(2, device=dev)
-        outs = [g_t[0].data_ptr()] + ([g_t[1].data_ptr()] if split else [])
+        outs = [x.data_ptr() for x in g_t]
         _lib.call(name, t.data_ptr(), lrfs.data_ptr(), act.data_ptr(), alpha.data_ptr(), beta.data_ptr(),
                   f[2].data_ptr(), f[3].data_ptr(), Gp.data_ptr(), Ga.data_ptr(), *outs, g_l.data_ptr(),
                   g_a.data_ptr(), g_ab.data_ptr(), B * P, K, I, O, T, st)
@@ -390,16 +392,17 @@ def test_routing_fused_packed_vs_scalar_and_split(B, P, K, I, O, T):
     assert quat_err(fp[0].cpu(), fs[0].cpu()) < 2e-6 and max_err(fp[1].cpu(), fs[1].cpu()) < 2e-6
     assert quat_err(fp[2].cpu(), fs[2].cpu()) < 2e-6 and max_err(fp[3].cpu(), fs[3].cpu()) < 1e-5
     bp, bs = bwd("qec_routing_fused_bwd", fs), bwd("qec_routing_fused_bwd_scalar", fs)
+    bp, bs = ([bp[0][0]] + list(bp[1:])), ([bs[0][0]] + list(bs[1:]))
     for k, (x, y) in enumerate(zip(bp, bs)):
         assert torch.isfinite(x).all(), k
         # dL/dlrfs keeps the radial component the normalisation projects out of dL/dt: it inherits the
         # 1/gap conditioning of the adjoint solve, so the two summation orders differ by ~1e-4 there
         assert rel_err(x.cpu(), y.cpu()) < (5e-4 if k == 1 else 2e-5), (k, rel_err(x.cpu(), y.cpu()))
     sp = bwd("qec_routing_fused_bwd_split", fs, split=True)
-    hi, lo = sp[0][0], sp[0][1]
+    hi, lo, g = sp[0][0], sp[0][1].float(), bp[0]
     assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0          # hi is on the TF32 grid
-    assert torch.equal(hi + lo, bp[0][0])                                  # exact split of the same gradient
-    assert float(lo.abs().max()) <= float(bp[0][0].abs().max()) * 2.0 ** -11
+    assert bool(((hi - g).abs() <= g.abs() * 2.0 ** -11).all())           # nearest TF32 value of the same gradient
+    assert bool(((hi + lo - g).abs() <= g.abs() * 2.0 ** -19 + 1e-37).all())   # BF16 remainder: ~2^-20 |g| left
 
 
 def test_transform_routing_node_matches_plain_path():
