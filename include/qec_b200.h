@@ -156,6 +156,28 @@ int qec_routing_fused_bwd_split(const float* t_oqi, const float* lrfs, const flo
                                 const float* g_agreement, float* g_toqi_hi, unsigned short* g_toqi_lo, float* g_lrfs,
                                 float* g_act, float* g_alpha_beta, int BP, int K, int I, int O, int T, void* stream);
 
+/* Operand preparation for the quater_gen2 GEMMs on the tensor cores at FP32 accuracy ("3xTF32";
+ * reference: nn.Linear in models/qec_module.py:124 and its autograd backward, FP32 cuBLAS SGEMM).
+ * qec_split_operand: src [R, C] (+ one extra column when add_col: extra[R] if given, else
+ *   extra_const -- the bias / the column of ones that folds the bias into the GEMM) = Kc real columns.
+ *   out_f32 [R, WT] (nullable): nblk <= 3 blocks at stride BS >= Kc, block j = the TF32 hi part
+ *   (blkj == 1) or the lo part (blkj == 2), zeros elsewhere; out_bf16 [R, WB] (nullable): the hi part in
+ *   BF16, zero-padded.  Output row r is read from source row perm[r] when perm (int64 [R]) is given.
+ * qec_fold_chunks: a [S, R, 2*KP], b [S, R, KP] split-K partial products -> out_main [*, ld_main] and
+ *   (ld_main == K - 1) column K - 1 -> out_last [*] (nullable = dropped); row r lands in row perm[r]. */
+int qec_split_operand(const float* src, const float* extra, float extra_const, const long long* perm,
+                      float* out_f32, unsigned short* out_bf16, long long R, int C, int add_col, int BS, int WT,
+                      int WB, int blk0, int blk1, int blk2, int nblk, void* stream);
+int qec_fold_chunks(const float* a, const float* b, const long long* perm, float* out_main, float* out_last, int S,
+                    long long R, int KP, int K, int ld_main, void* stream);
+
+/* Spread loss of QEC-Net and its gradient in one launch pair (reference models/qec_net.py:53-59,
+ * margin 0.1): loss [1] = mean_b sum_{c != y_b} relu(m - (x[b,y_b] - x[b,c]))^2, g_x [B, C] = dloss/dx.
+ * scratch: B floats.  err: device int set to 1 if a label is outside [0, C) (the reference's
+ * scatter_ raises). */
+int qec_spread_loss(const float* x, const long long* labels, float margin, float* loss, float* g_x, float* scratch,
+                    int* err, int B, int C, void* stream);
+
 /* FP32 FMA roof: blocks*256 threads x iters x 16 dependent-chain FMAs
  * (2*16*iters*256*blocks FLOP); timed by the caller with CUDA events.  No reference
  * counterpart: it measures the denominator of the FP32 roofline on the box. */

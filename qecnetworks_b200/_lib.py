@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_PKG, "libqec_b200.so")
 _P = ctypes.c_void_p
 _I = ctypes.c_int
 _LL = ctypes.c_longlong
+_F = ctypes.c_float
 
 # name -> (argtypes, kernels launched per call)
 SIGNATURES = {
@@ -35,6 +36,9 @@ SIGNATURES = {
     "qec_symeig4_fwd": ([_P, _P, _P, _P, _LL, _P], 1),
     "qec_symeig4_bwd": ([_P, _P, _P, _P, _P, _LL, _I, _P], 1),
     "qec_gather": ([_P] * 9 + [_I, _I, _I, _I, _I, _P], 1),
+    "qec_split_operand": ([_P, _P, _F, _P, _P, _P, _LL, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], 1),
+    "qec_fold_chunks": ([_P, _P, _P, _P, _P, _I, _LL, _I, _I, _I, _P], 1),
+    "qec_spread_loss": ([_P, _P, _F, _P, _P, _P, _P, _I, _I, _P], 2),
     "qec_ffma_peak": ([_P, _I, _I, _P], 1),
     "qec_pipe_probe": ([_P, _I, _I, _I, _P], 1),
 }

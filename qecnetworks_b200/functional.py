@@ -196,6 +196,68 @@ class RoutingFused(torch.autograd.Function):
         return g_toqi, g_lrfs, g_act, g_ab[0:1], g_ab[1:2], None
 
 
+def split_operand(src, extra=None, extra_const=1.0, perm=None, add_col=True, blocks=(1, 1, 2), stride=None, width=None,
+                  bf16_width=None):
+    """[src | extra column] -> (out_f32 | None, out_bf16 | None): the 3xTF32 GEMM operand built in one launch
+    (qec_split_operand): `blocks` (1 = TF32 hi part, 2 = lo part) at block stride `stride`, zero-padded to
+    `width`; and/or the hi part in BF16 padded to `bf16_width`.  Row r comes from src[perm[r]]."""
+    src = _check(src, "src", tuple(src.shape))
+    R, C = src.shape
+    Kc = C + (1 if add_col else 0)
+    dev = src.device
+    if extra is not None:
+        extra = _check(extra, "extra", (R,))
+    if perm is not None:
+        if perm.dtype != torch.int64 or not perm.is_cuda:
+            raise TypeError("perm must be a CUDA int64 tensor")
+        perm = perm.contiguous()
+    nblk = len(blocks) if width is not None else 0
+    stride = Kc if stride is None else int(stride)
+    out = torch.empty(R, int(width), device=dev, dtype=torch.float32) if width is not None else None
+    outb = torch.empty(R, int(bf16_width), device=dev, dtype=torch.bfloat16) if bf16_width is not None else None
+    blk = list(blocks) + [0, 0, 0]
+    call("qec_split_operand", ptr(src), ptr(extra), float(extra_const), ptr(perm), ptr(out), ptr(outb), R, C,
+         1 if add_col else 0, stride, int(width or 0), int(bf16_width or 0), blk[0], blk[1], blk[2], nblk, _stream())
+    return out, outb
+
+
+def fold_chunks(a, b, perm, out_main, out_last, K):
+    """out_main[perm[r], c] = sum_s a[s,r,c] + a[s,r,KP+c] + b[s,r,c] (c < out_main width); column K-1 goes to
+    out_last when out_main is K-1 wide (qec_fold_chunks)"""
+    S, R, KP2 = a.shape
+    KP = KP2 // 2
+    call("qec_fold_chunks", ptr(a), ptr(b), ptr(perm), ptr(out_main), ptr(out_last), S, R, KP, K, out_main.shape[1],
+         _stream())
+
+
+class SpreadLoss(torch.autograd.Function):
+    """spread loss of QEC-Net (reference models/qec_net.py:53-59) with its gradient in one launch pair"""
+
+    @staticmethod
+    def forward(ctx, x, target, margin):
+        B, C = x.shape
+        x = _check(x, "x", (B, C))
+        target = target.to(device=x.device, dtype=torch.int64).contiguous().view(B)
+        loss = torch.empty(1, device=x.device, dtype=torch.float32)
+        g = torch.empty_like(x)
+        scratch = torch.empty(B, device=x.device, dtype=torch.float32)
+        err = torch.zeros(1, device=x.device, dtype=torch.int32)
+        call("qec_spread_loss", ptr(x), ptr(target), float(margin), ptr(loss), ptr(g), ptr(scratch), ptr(err), B, C,
+             _stream())
+        ctx.save_for_backward(g)
+        ctx.err = err  # checked lazily by callers that can afford a sync (spread_loss(..., check=True))
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        (g,) = ctx.saved_tensors
+        return g * g_loss, None, None
+
+
+def spread_loss(x, target, margin=0.1):
+    return SpreadLoss.apply(x, target, margin)
+
+
 def routing_fused_packed_supported(K, I, O, T):
     return bool(_lib.query("qec_routing_fused_packed_supported", int(K), int(I), int(O), int(T)))
 

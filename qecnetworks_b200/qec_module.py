@@ -73,71 +73,72 @@ def _chunks(n, length=1024):
     return s
 
 
-def _split_tf32_grads(g_hi, g_lo, xa, wa, need_x, need_w):
-    """g_xa = g @ wa and g_wa = g^T @ xa for g = g_hi + g_lo delivered pre-split by the routing backward
-    (g_hi float32 on the TF32 grid, g_lo the remainder in bfloat16), on the tensor cores at FP32 accuracy:
-        g @ w = g_hi (w_hi + w_lo) + g_lo w_hi        (the lo*lo term is ~2^-22 relative)
-    with the first product a TF32 GEMM over [w_hi | w_lo] and the second a BF16 GEMM.  The long
-    contraction (20 480 resp. 8 192 terms) is cut into chunks of ~1 000 whose partial products are summed
-    in FP32, because the tensor-core accumulator alone loses ~5e-5 over such lengths; with the chunks the
-    error (1e-6 .. 6e-6 of the largest entry) is that of the SIMT SGEMM it replaces (3e-6 .. 6e-6) at
-    40 % of its time (scripts/gemm_probe7.py: 430 us vs 1 090 us for both products)."""
-    M, N = g_hi.shape
-    K = xa.shape[1]
-    KP = K + ((-K) % 8)
-
-    def blocks(t):
-        hi = _tf32_round(t)
-        lo = _tf32_round(t - hi)
-        z = t.new_zeros(t.shape[0], KP - K)
-        return torch.cat([hi, z, lo, z], dim=1), torch.cat([hi, z], dim=1).to(torch.bfloat16)
-
+def _tf32_mm(fn, *args, **kw):
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
     try:
-        g_xa = g_wa = None
-        if need_w:
-            S = _chunks(M)
-            X0, X1 = blocks(xa)
-            a = torch.bmm(g_hi.view(S, M // S, N).transpose(1, 2), X0.view(S, M // S, 2 * KP)).sum(0)
-            b = torch.bmm(g_lo.view(S, M // S, N).transpose(1, 2), X1.view(S, M // S, KP),
-                          out_dtype=torch.float32).sum(0)
-            g_wa = a[:, :K] + a[:, KP:KP + K] + b[:, :K]
-        if need_x:
-            S = _chunks(N)
-            W0, W1 = blocks(wa)
-            a = torch.bmm(g_hi.view(M, S, N // S).transpose(0, 1), W0.view(S, N // S, 2 * KP)).sum(0)
-            b = torch.bmm(g_lo.view(M, S, N // S).transpose(0, 1), W1.view(S, N // S, KP),
-                          out_dtype=torch.float32).sum(0)
-            g_xa = a[:, :K] + a[:, KP:KP + K] + b[:, :K]
+        return fn(*args, **kw)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
-    return g_xa, g_wa
 
 
 class _TransformRoutingFused(torch.autograd.Function):
-    """quater_gen2 (as xa @ wa^T, capsule-major rows) + the cluster-resident routing kernels as ONE
-    autograd node, so that the 671 MB gradient of the transforms can travel from the routing backward
-    to the two weight/input-gradient GEMMs pre-split for the tensor cores (never as a plain FP32
-    tensor): reference qec_module.py:124 + 126-147 + 172-194."""
+    """quater_gen2 (t = [h, 1] @ [W2, b2]^T with the rows of W2 in capsule-major order) + the cluster-resident
+    routing kernels as ONE autograd node (reference qec_module.py:124 + 126-147 + 172-194), so that
+
+    * the GEMM operands are built by one launch each (qec_split_operand: bias column, row permutation, TF32
+      hi/lo split, padding) instead of ~17 ATen launches, and the forward is one 3xTF32 tensor-core GEMM
+      [h_hi | h_hi | h_lo] @ [w_hi | w_lo | w_hi]^T (K = 3*41 -> 128): 122 us instead of 466 us for the SIMT
+      SGEMM, max error 9e-7 of the largest entry;
+    * the 671 MB gradient of the transforms travels from the routing backward to the two weight / input
+      gradient GEMMs pre-split for the tensor cores (TF32 hi plane + BF16 remainder), never as a plain FP32
+      tensor:  g @ w = g_hi (w_hi + w_lo) + g_lo w_hi  -- a TF32 bmm and a BF16 bmm per product, with the
+      long contraction (20 480 resp. 8 192 terms) cut into chunks of ~1 000 whose partial products are
+      summed in FP32 (the tensor-core accumulator alone loses ~5e-5 over such lengths).  Error 1e-6 .. 6e-6
+      of the largest entry, the same as the SIMT SGEMM it replaces, at 40 % of its time
+      (scripts/gemm_probe7.py: 430 us vs 1 090 us for both products);
+    * qec_fold_chunks sums the partial products and scatters them straight into dL/dW2 (rows permuted
+      back), dL/db2 and dL/dh."""
 
     @staticmethod
-    def forward(ctx, xa, wa, lrfs, activation, alpha, beta, num_iterations):
+    def forward(ctx, h, W2, b2, perm, lrfs, activation, alpha, beta, num_iterations):
         T = int(num_iterations)
-        t_oqi = _split_tf32_matmul(xa, wa)
+        K = h.shape[1] + 1
+        W3 = 3 * K + ((-3 * K) % 16)  # tensor-core kernels need an aligned contraction length
+        A, _ = QF.split_operand(h, None, 1.0, None, True, (1, 1, 2), K, W3)
+        Bm, _ = QF.split_operand(W2, b2, 0.0, perm, True, (1, 2, 1), K, W3)
+        t_oqi = _tf32_mm(torch.matmul, A, Bm.t())
         pose, agreement, poses_all, stats = QF.routing_fused_forward_raw(t_oqi, lrfs, activation, alpha, beta, T)
-        ctx.save_for_backward(xa, wa, t_oqi, lrfs, activation, alpha, beta, poses_all, stats)
+        ctx.save_for_backward(h, W2, b2, perm, t_oqi, lrfs, activation, alpha, beta, poses_all, stats)
         ctx.T = T
         return pose, agreement
 
     @staticmethod
     def backward(ctx, g_pose, g_agreement):
-        xa, wa, t_oqi, lrfs, activation, alpha, beta, poses_all, stats = ctx.saved_tensors
+        h, W2, b2, perm, t_oqi, lrfs, activation, alpha, beta, poses_all, stats = ctx.saved_tensors
         (g_hi, g_lo), g_lrfs, g_act, g_ab = QF.routing_fused_backward_raw(
             t_oqi, lrfs, activation, alpha, beta, poses_all, stats, g_pose, g_agreement, ctx.T,
-            ctx.needs_input_grad[2], ctx.needs_input_grad[3], split=True)
-        g_xa, g_wa = _split_tf32_grads(g_hi, g_lo, xa, wa, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
-        return g_xa, g_wa, g_lrfs, g_act, g_ab[0:1], g_ab[1:2], None
+            ctx.needs_input_grad[4], ctx.needs_input_grad[5], split=True)
+        M, N = g_hi.shape
+        K = h.shape[1] + 1
+        KP = K + ((-K) % 8)
+        g_h = g_W2 = g_b2 = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:  # dL/d[W2, b2] = g^T @ [h, 1]
+            S = _chunks(M)
+            X0, X1 = QF.split_operand(h, None, 1.0, None, True, (1, 2), KP, 2 * KP, KP)
+            a = _tf32_mm(torch.bmm, g_hi.view(S, M // S, N).transpose(1, 2), X0.view(S, M // S, 2 * KP))
+            b = torch.bmm(g_lo.view(S, M // S, N).transpose(1, 2), X1.view(S, M // S, KP), out_dtype=torch.float32)
+            g_W2 = torch.empty_like(W2)
+            g_b2 = torch.empty_like(b2)
+            QF.fold_chunks(a, b, perm, g_W2, g_b2, K)
+        if ctx.needs_input_grad[0]:  # dL/dh = g @ [W2, b2] (the column of the bias is dropped)
+            S = _chunks(N)
+            W0, W1 = QF.split_operand(W2, b2, 0.0, perm, True, (1, 2), KP, 2 * KP, KP)
+            a = _tf32_mm(torch.bmm, g_hi.view(M, S, N // S).transpose(0, 1), W0.view(S, N // S, 2 * KP))
+            b = torch.bmm(g_lo.view(M, S, N // S).transpose(0, 1), W1.view(S, N // S, KP), out_dtype=torch.float32)
+            g_h = torch.empty_like(h)
+            QF.fold_chunks(a, b, None, g_h, None, K)
+        return g_h, g_W2, g_b2, None, g_lrfs, g_act, g_ab[0:1], g_ab[1:2], None
 
 
 def _augment(x, weight, bias, row_perm=None):
@@ -207,9 +208,9 @@ class QecModule(Module):
         if K * I >= self.FUSED_MIN_VOTES and QF.routing_fused_supported(K, I, O, self.num_iterations):
             # capsule-major transforms straight out of the GEMM; votes never touch HBM
             if QF.routing_fused_packed_supported(K, I, O, self.num_iterations):
-                xa, wa = _augment(h, self.quater_gen2.weight, self.quater_gen2.bias, self._oqi_perm(I, O))
-                pose, agreement = _TransformRoutingFused.apply(xa, wa, lrfs, act_flat, self.alpha, self.beta,
-                                                               self.num_iterations)
+                pose, agreement = _TransformRoutingFused.apply(
+                    h, self.quater_gen2.weight, self.quater_gen2.bias, self._oqi_perm(I, O), lrfs, act_flat,
+                    self.alpha, self.beta, self.num_iterations)
             else:
                 t_oqi = _linear_bias_in_gemm(h, self.quater_gen2.weight, self.quater_gen2.bias,
                                              self._oqi_perm(I, O))

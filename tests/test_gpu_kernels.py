@@ -423,13 +423,15 @@ def test_transform_routing_node_matches_plain_path():
     Gp = torch.randn(B, P, O, 4, generator=gen).to(dev)
     Ga = torch.randn(B, P, O, generator=gen).to(dev)
 
+    perm = _oqi_perm(I, O).to(dev)
+
     def run(node):
         hh, WW, bb = (x.clone().requires_grad_(True) for x in (h, W, b))
         ll, aa = lrfs.clone().requires_grad_(True), act.clone().requires_grad_(True)
-        xa, wa = QM._augment(hh, WW, bb)
         if node:
-            pose, agr = QM._TransformRoutingFused.apply(xa, wa, ll, aa, alpha, beta, T)
+            pose, agr = QM._TransformRoutingFused.apply(hh, WW, bb, perm, ll, aa, alpha, beta, T)
         else:
+            xa, wa = QM._augment(hh, WW, bb, perm)
             pose, agr = QF.routing_fused(QM._SplitTf32Matmul.apply(xa, wa), ll, aa, alpha, beta, T)
         ((pose * Gp).sum() + (agr * Ga).sum()).backward()
         return pose.detach(), agr.detach(), hh.grad, WW.grad, bb.grad, ll.grad, aa.grad
@@ -438,6 +440,27 @@ def test_transform_routing_node_matches_plain_path():
     assert quat_err(a[0].cpu(), c[0].cpu()) < 1e-6 and max_err(a[1].cpu(), c[1].cpu()) < 1e-6
     for k in range(2, 7):
         assert rel_err(a[k].cpu(), c[k].cpu()) < (5e-4 if k == 5 else 2e-5), (k, rel_err(a[k].cpu(), c[k].cpu()))
+
+
+def test_spread_loss_kernel():
+    """qec_spread_loss against the reference expression (models/qec_net.py:53-59), value and gradient"""
+    from qecnetworks_b200 import functional as QF
+
+    dev = cuda()
+    gen = torch.Generator().manual_seed(11)
+    for B, C in [(32, 40), (5, 10), (1, 3), (64, 70)]:
+        x = torch.rand(B, C, generator=gen) * 0.3 + 0.5
+        y = torch.randint(0, C, (B,), generator=gen)
+        xr = x.clone().double().requires_grad_(True)
+        onehot = torch.zeros(B, C, dtype=torch.double).scatter_(1, y.view(-1, 1), 1.0)
+        at = (xr * onehot).sum(1)
+        ref = ((torch.relu(0.1 - (at.view(-1, 1) - xr)) ** 2) * (1 - onehot)).sum(1).mean()
+        ref.backward()
+        xd = x.to(dev).requires_grad_(True)
+        loss = QF.spread_loss(xd, y.to(dev), 0.1)
+        (loss * 3.0).backward()
+        assert abs(float(loss) - float(ref)) < 1e-6
+        assert max_err(xd.grad.cpu(), 3.0 * xr.grad) < 1e-6
 
 
 # ---------------------------------------------------------------- register-resident pool1 kernel
