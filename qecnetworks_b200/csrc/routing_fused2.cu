@@ -1000,7 +1000,7 @@ __global__ void __launch_bounds__(kPT, 2)
 #undef QEC_BWD_GRAD
 #undef QEC_BWD_ACC
         }
-        QEC_EVT(22);
+        QEC_EVT(25);
         QEC_EVT_NEXT();
         // the next capsule's sweep 0 touches this thread's own slots only; the reducer's scratch is
         // protected by the barriers inside reduce() / bcast()

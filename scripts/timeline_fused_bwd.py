@@ -17,8 +17,8 @@ lib.qec_prof_read(buf.ctypes.data)
 ev = buf.reshape(8, 64, 32)
 names = {0: "sweep0 start", 1: "sweep0 end", 2: "r0: cta barrier", 3: "r0: pushed", 4: "r0: totals", 5: "solve0 done", 6: "sync0 done",
          7: "grad pass end", 8: "acc(2) end", 9: "r1: cta barrier", 10: "r1: pushed", 11: "r1: totals", 12: "solve1 done", 13: "sync1 done",
-         15: "acc(1) end", 16: "r2: cta barrier", 17: "r2: pushed", 18: "r2: totals", 19: "solve2 done", 20: "sync2 done", 22: "acc(0) end"}
-order = sorted(names)
+         15: "acc(1) end", 16: "r2: cta barrier", 17: "r2: pushed", 18: "r2: totals", 19: "solve2 done", 20: "sync2 done", 25: "acc(0) end", 22: "r0: summed16", 23: "r0: butterfly", 24: "r0: mbar done"}
+order = [0, 1, 2, 22, 23, 3, 24, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15, 16, 17, 18, 19, 20, 25]
 for blk in (0,):
     d = ev[blk, 2:30, :].astype(np.float64)
     rel = d - d[:, 0:1]
