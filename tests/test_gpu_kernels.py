@@ -342,7 +342,19 @@ def test_routing_fused(B, P, K, I, O, T):
     assert max_err(agr.detach().cpu(), agr2.detach().cpu()) < 1e-5
 
 
-@pytest.mark.parametrize("B,P,K,I,O,T", [(2, 1, 256, 128, 3, 3), (1, 2, 100, 30, 3, 3), (2, 1, 37, 6, 5, 1), (1, 1, 1, 2, 1, 3)])
+@pytest.mark.parametrize(
+    "B,P,K,I,O,T",
+    [
+        (2, 1, 256, 128, 3, 3),   # cluster of 8, every CTA full (the guard-free instantiation)
+        (1, 1, 256, 128, 3, 2),   # ... T = 2
+        (1, 1, 128, 128, 2, 3),   # cluster of 4, full
+        (1, 1, 64, 128, 2, 3),    # cluster of 2, full
+        (1, 2, 32, 128, 2, 3),    # one CTA per capsule, full
+        (1, 2, 100, 30, 3, 3),    # ragged
+        (2, 1, 37, 6, 5, 1),      # T = 1, tiny
+        (1, 1, 1, 2, 1, 3),       # a single pair, one of its votes dead
+    ],
+)
 def test_routing_fused_packed_vs_scalar_and_split(B, P, K, I, O, T):
     """the packed-pair kernels (routing_fused2.cu) against the scalar ones (routing_fused.cu) through the
     C ABI on the same inputs, incl. a capsule with a single live vote (|<pose, vote>| = 1: the distance
