@@ -11,10 +11,68 @@ forward is the B200 kernel pipeline instead of the ATen op sequence:
 No host synchronisation anywhere (the reference syncs 2(1+T) times per forward:
 nonzero() and cuSOLVER's info copy).
 """
+import threading
+
 import torch
 from torch.nn import Linear, Module, Parameter
 
 from . import functional as QF
+
+
+# The TF32 switch of cuBLAS is process-global in PyTorch (torch.backends.cuda.matmul.allow_tf32) while
+# the reference's multi-GPU mode, nn.DataParallel (train_cls.py:27), runs one Python thread per GPU
+# through this module.  Every matmul this package issues therefore goes through _mm(): one lock, the
+# switch set explicitly to what that product needs (on for the pre-split 3xTF32 products, OFF for the
+# plain FP32 ones) and restored afterwards, so no product of ours can be launched with another
+# thread's setting.  (The switch is read at launch time; the kernels themselves run asynchronously.)
+_MM_LOCK = threading.Lock()
+
+
+def _mm(tf32, fn, *args, **kw):
+    with _MM_LOCK:
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
+        try:
+            return fn(*args, **kw)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+class _LinearFP32(torch.autograd.Function):
+    """F.linear in plain FP32 (quater_gen1, reference qec_module.py:123), forward and backward under _mm()"""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return _mm(False, torch.addmm, bias, x, weight.t())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = g.contiguous()
+        g_x = _mm(False, torch.mm, g, weight) if ctx.needs_input_grad[0] else None
+        g_w = _mm(False, torch.mm, g.t(), x) if ctx.needs_input_grad[1] else None
+        g_b = g.sum(0) if ctx.needs_input_grad[2] else None
+        return g_x, g_w, g_b
+
+
+class _ComposeFP32(torch.autograd.Function):
+    """(W1, b1, W2, b2) -> (Wc = W2 W1, bc = W2 b1 + b2): the two Linears of get_votes composed (no
+    non-linearity between them, reference qec_module.py:123-124); plain FP32 under _mm() both ways"""
+
+    @staticmethod
+    def forward(ctx, W1, b1, W2, b2):
+        ctx.save_for_backward(W1, b1, W2)
+        return _mm(False, torch.mm, W2, W1), _mm(False, torch.addmv, b2, W2, b1)
+
+    @staticmethod
+    def backward(ctx, g_Wc, g_bc):
+        W1, b1, W2 = ctx.saved_tensors
+        g_Wc, g_bc = g_Wc.contiguous(), g_bc.contiguous()
+        g_W1 = _mm(False, torch.mm, W2.t(), g_Wc)
+        g_b1 = _mm(False, torch.mv, W2.t(), g_bc)
+        g_W2 = _mm(False, torch.addmm, torch.outer(g_bc, b1), g_Wc, W1.t())
+        return g_W1, g_b1, g_W2, g_bc
 
 
 def _tf32_round(x):
@@ -40,13 +98,7 @@ def _split_tf32_matmul(xa, wa):
     wl = _tf32_round(wa - wh)
     A = torch.cat([xh, xh, xl, xa.new_zeros(xa.shape[0], pad)], dim=1)
     Bm = torch.cat([wh, wl, wh, wa.new_zeros(wa.shape[0], pad)], dim=1)
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = True
-    try:
-        y = A @ Bm.t()
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = prev
-    return y
+    return _mm(True, torch.matmul, A, Bm.t())
 
 
 class _SplitTf32Matmul(torch.autograd.Function):
@@ -60,8 +112,8 @@ class _SplitTf32Matmul(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         xa, wa = ctx.saved_tensors
-        g_xa = g @ wa if ctx.needs_input_grad[0] else None
-        g_wa = g.t() @ xa if ctx.needs_input_grad[1] else None
+        g_xa = _mm(False, torch.mm, g, wa) if ctx.needs_input_grad[0] else None
+        g_wa = _mm(False, torch.mm, g.t(), xa) if ctx.needs_input_grad[1] else None
         return g_xa, g_wa
 
 
@@ -71,15 +123,6 @@ def _chunks(n, length=1024):
     while n % (2 * s) == 0 and n // (2 * s) >= length:
         s *= 2
     return s
-
-
-def _tf32_mm(fn, *args, **kw):
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = True
-    try:
-        return fn(*args, **kw)
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = prev
 
 
 class _TransformRoutingFused(torch.autograd.Function):
@@ -107,7 +150,7 @@ class _TransformRoutingFused(torch.autograd.Function):
         W3 = 3 * K + ((-3 * K) % 16)  # tensor-core kernels need an aligned contraction length
         A, _ = QF.split_operand(h, None, 1.0, None, True, (1, 1, 2), K, W3)
         Bm, _ = QF.split_operand(W2, b2, 0.0, perm, True, (1, 2, 1), K, W3)
-        t_oqi = _tf32_mm(torch.matmul, A, Bm.t())
+        t_oqi = _mm(True, torch.matmul, A, Bm.t())
         pose, agreement, poses_all, stats = QF.routing_fused_forward_raw(t_oqi, lrfs, activation, alpha, beta, T)
         ctx.save_for_backward(h, W2, b2, perm, t_oqi, lrfs, activation, alpha, beta, poses_all, stats)
         ctx.T = T
@@ -126,16 +169,18 @@ class _TransformRoutingFused(torch.autograd.Function):
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:  # dL/d[W2, b2] = g^T @ [h, 1]
             S = _chunks(M)
             X0, X1 = QF.split_operand(h, None, 1.0, None, True, (1, 2), KP, 2 * KP, KP)
-            a = _tf32_mm(torch.bmm, g_hi.view(S, M // S, N).transpose(1, 2), X0.view(S, M // S, 2 * KP))
-            b = torch.bmm(g_lo.view(S, M // S, N).transpose(1, 2), X1.view(S, M // S, KP), out_dtype=torch.float32)
+            a = _mm(True, torch.bmm, g_hi.view(S, M // S, N).transpose(1, 2), X0.view(S, M // S, 2 * KP))
+            b = _mm(False, torch.bmm, g_lo.view(S, M // S, N).transpose(1, 2), X1.view(S, M // S, KP),
+                    out_dtype=torch.float32)
             g_W2 = torch.empty_like(W2)
             g_b2 = torch.empty_like(b2)
             QF.fold_chunks(a, b, perm, g_W2, g_b2, K)
         if ctx.needs_input_grad[0]:  # dL/dh = g @ [W2, b2] (the column of the bias is dropped)
             S = _chunks(N)
             W0, W1 = QF.split_operand(W2, b2, 0.0, perm, True, (1, 2), KP, 2 * KP, KP)
-            a = _tf32_mm(torch.bmm, g_hi.view(M, S, N // S).transpose(0, 1), W0.view(S, N // S, 2 * KP))
-            b = torch.bmm(g_lo.view(M, S, N // S).transpose(0, 1), W1.view(S, N // S, KP), out_dtype=torch.float32)
+            a = _mm(True, torch.bmm, g_hi.view(M, S, N // S).transpose(0, 1), W0.view(S, N // S, 2 * KP))
+            b = _mm(False, torch.bmm, g_lo.view(M, S, N // S).transpose(0, 1), W1.view(S, N // S, KP),
+                    out_dtype=torch.float32)
             g_h = torch.empty_like(h)
             QF.fold_chunks(a, b, None, g_h, None, K)
         return g_h, g_W2, g_b2, None, g_lrfs, g_act, g_ab[0:1], g_ab[1:2], None
@@ -199,12 +244,11 @@ class QecModule(Module):
             # register-resident kernel evaluate Wc x + bc per vote -- no [B*P*K, 4*O] tensor, no GEMM
             W1, b1 = self.quater_gen1.weight, self.quater_gen1.bias
             W2, b2 = self.quater_gen2.weight, self.quater_gen2.bias
-            Wc = W2 @ W1
-            bc = torch.addmv(b2, W2, b1)
+            Wc, bc = _ComposeFP32.apply(W1, b1, W2, b2)
             pose, agreement = QF.routing_small(xrot, lrfs, act_flat, Wc, bc, self.alpha, self.beta,
                                                self.num_iterations)
             return pose.squeeze(-2), agreement
-        h = self.quater_gen1(xrot.view(B * P * K, 3 * I))
+        h = _LinearFP32.apply(xrot.view(B * P * K, 3 * I), self.quater_gen1.weight, self.quater_gen1.bias)
         if K * I >= self.FUSED_MIN_VOTES and QF.routing_fused_supported(K, I, O, self.num_iterations):
             # capsule-major transforms straight out of the GEMM; votes never touch HBM
             if QF.routing_fused_packed_supported(K, I, O, self.num_iterations):
