@@ -10,8 +10,9 @@
 //
 //  * Votes are processed as PAIRS (j, j+1) = inputs (k, i), (k, i+1) held in the low / high half
 //    of 64-bit register pairs and every FP32 operation of a sweep is one FFMA2 / FMUL2 /
-//    FADD2 for both (f32x2.cuh).  A routing sweep costs ~21 issue slots per vote instead of
-//    ~40.  Shared memory keeps the pair component-interleaved, {w0 w1 x0 x1} {y0 y1 z0 z1},
+//    FADD2 for both (f32x2.cuh).  A routing sweep costs 23.5 issue slots per vote instead of
+//    ~40 (FFMA2 = one issue slot, two fma-pipe cycles: the bound moves from issue to the fma
+//    pipe).  Shared memory keeps the pair component-interleaved, {w0 w1 x0 x1} {y0 y1 z0 z1},
 //    so a pair is two conflict-free LDS.128 straight into aligned register pairs; the
 //    transforms arrive the same way with LDG.64 / 8-byte cp.async because i is the
 //    contiguous axis of the capsule-major transform layout t_oqi.
@@ -19,8 +20,13 @@
 //    into the vote slots while the epilogue sweep of the current capsule frees them, one
 //    commit group per slot, so HBM latency hides behind the epilogue sweep and the first
 //    reduction instead of stalling sweep 0.
-//  * The epilogue's two sums ride in the next capsule's first reduction (15 of the 16 lanes
-//    of the reducer), so a capsule costs T cluster reductions instead of T + 1.
+//  * The epilogue's two sums ride in the next capsule's first reduction (15 values wide), so a
+//    capsule costs T cluster reductions instead of T + 1.
+//  * The cluster reduction needs no cluster barrier (PushReducer below: st.async pushes into the
+//    peers' receive buffers, completion counted by their mbarriers).
+//  * Backward: packed twin of routing_fused_bwd_kernel; the top level is two passes so that neither
+//    spills; dL/dt can leave pre-split for the tensor-core GEMMs that consume it (TF32 plane +
+//    BF16 remainder, qec_routing_fused_bwd_split).
 //
 // Requires I even (pairs never straddle a neighbour row and stay 8-byte aligned); other
 // geometries use the scalar kernels of routing_fused.cu.
