@@ -118,6 +118,29 @@ def test_net_vs_oracle_seeded():
     assert grads_close(got, {k: p64[k].grad for k in got}, TOL) == []
 
 
+def test_net_vs_oracle_full_geometry():
+    """BASELINE config 2 geometry per sample (C=128, 40 classes, T=3: pool1 = 256 x 9 votes per capsule,
+    pool2 = 32 768 votes per capsule on the full 8-CTA clusters of the packed kernels) at B=2 against the
+    float64 oracle: outputs and every parameter gradient."""
+    import qecnetworks_b200 as qb
+
+    dev = cuda()
+    params = orc.init_net_params(128, 40, seed=9)
+    points, lrfs, act, labels = orc.synthetic_batch(2, ncls=40, seed=33)
+    p64 = {k: v.double().requires_grad_(True) for k, v in params.items()}
+    pose_ref, a_ref = orc.qec_net_forward(p64, points.double(), lrfs.double(), act.double(), 3)
+    orc.spread_loss(a_ref, labels).backward()
+    net = qb.QecNet(2048, 128, 40, 3)
+    net.load_state_dict(params)
+    net = net.to(dev)
+    pose, a = net(points.to(dev), lrfs.to(dev), act.to(dev), None)
+    assert quat_err(pose.cpu(), pose_ref) < TOL
+    assert max_err(a.cpu(), a_ref) < TOL
+    net.spread_loss(a, labels.to(dev)).backward()
+    got = {k: v.grad.cpu() for k, v in net.named_parameters()}
+    assert grads_close(got, {k: p64[k].grad for k in got}, TOL) == []
+
+
 def test_full_size_properties():
     """BASELINE config 2 shapes (B=32, C=128, 40 classes, T=3): size-independent
     properties -- unit-norm poses in the w>=0 hemisphere, activations in (0,1),
