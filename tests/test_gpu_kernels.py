@@ -388,7 +388,7 @@ def test_routing_fused_packed_vs_scalar_and_split(B, P, K, I, O, T):
                   pose.data_ptr(), agr.data_ptr(), pa.data_ptr(), stt.data_ptr(), B * P, K, I, O, T, st)
         return pose, agr, pa, stt
 
-    def bwd(name, f, split=False):
+    def bwd(name, f, split=False, chain=True):
         g_t = [torch.full(tuple(t.shape), 7.0, device=dev)]
         if split:
             g_t.append(torch.full(tuple(t.shape), 7.0, device=dev, dtype=torch.bfloat16))
@@ -396,7 +396,7 @@ def test_routing_fused_packed_vs_scalar_and_split(B, P, K, I, O, T):
         outs = [x.data_ptr() for x in g_t]
         _lib.call(name, t.data_ptr(), lrfs.data_ptr(), act.data_ptr(), alpha.data_ptr(), beta.data_ptr(),
                   f[2].data_ptr(), f[3].data_ptr(), Gp.data_ptr(), Ga.data_ptr(), *outs, g_l.data_ptr(),
-                  g_a.data_ptr(), g_ab.data_ptr(), B * P, K, I, O, T, st)
+                  g_a.data_ptr() if chain else None, g_ab.data_ptr(), B * P, K, I, O, T, st)
         torch.cuda.synchronize()
         return g_t, g_l, g_a, g_ab
 
@@ -410,6 +410,10 @@ def test_routing_fused_packed_vs_scalar_and_split(B, P, K, I, O, T):
         # dL/dlrfs keeps the radial component the normalisation projects out of dL/dt: it inherits the
         # 1/gap conditioning of the adjoint solve, so the two summation orders differ by ~1e-4 there
         assert rel_err(x.cpu(), y.cpu()) < (5e-4 if k == 1 else 2e-5), (k, rel_err(x.cpu(), y.cpu()))
+    # activation without gradient (pool1-like callers): only the top level is processed
+    np_, ns_ = bwd("qec_routing_fused_bwd", fs, chain=False), bwd("qec_routing_fused_bwd_scalar", fs, chain=False)
+    assert rel_err(np_[0][0].cpu(), ns_[0][0].cpu()) < 2e-5 and rel_err(np_[1].cpu(), ns_[1].cpu()) < 5e-4
+    assert float(np_[2].abs().max()) == 0.0
     sp = bwd("qec_routing_fused_bwd_split", fs, split=True)
     hi, lo, g = sp[0][0], sp[0][1].float(), bp[0]
     assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0          # hi is on the TF32 grid
