@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kST)
 // backward for the case where only the parameters need gradients (pool1: the LRFs, points and
 // 0/1 activations are data): dL/dWc [4O,3], dL/dbc [4O], dL/dalpha, dL/dbeta, all ACCUMULATED.
 template <int KMAX>
-__global__ void __launch_bounds__(kST)
+__global__ void __launch_bounds__(kST, 4)
     routing_small_bwd_kernel(const float* __restrict__ xrot, const float* __restrict__ lrfs,
                              const float* __restrict__ act, const float* __restrict__ Wc,
                              const float* __restrict__ bc, const float* __restrict__ alpha_p,
@@ -259,9 +259,17 @@ __global__ void __launch_bounds__(kST)
 
 static int small_kmax(int K) { return K <= 9 ? 9 : (K <= 16 ? 16 : 0); }
 
-static dim3 small_grid(int BP, int O) {
+// persistent grid: exactly as many CTAs as are co-resident (one wave), each walking over many patches
+template <class Kern>
+static dim3 small_grid(Kern kern, int BP, int O, int& cached_per_sm) {
     const int gy = (O + kST - 1) / kST;
-    int gx = (kNumSMs * 8 + gy - 1) / gy;  // a few CTAs per SM; each walks over many patches
+    if (cached_per_sm < 0) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kST, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+        cached_per_sm = per_sm;
+    }
+    int gx = (kNumSMs * cached_per_sm) / gy;
+    if (gx < 1) gx = 1;
     if (gx > BP) gx = BP;
     return dim3((unsigned)gx, (unsigned)gy);
 }
@@ -287,7 +295,9 @@ extern "C" int qec_routing_small_fwd(const float* xrot, const float* lrfs, const
     QEC_CHECK_ARG(BP > 0, 12);
     QEC_CHECK_ARG(qec_routing_small_supported(K, 1, O, T), 13);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const dim3 grid = small_grid(BP, O);
+    static int occ9 = -1, occ16 = -1;
+    const dim3 grid = (small_kmax(K) == 9) ? small_grid(routing_small_fwd_kernel<9>, BP, O, occ9)
+                                           : small_grid(routing_small_fwd_kernel<16>, BP, O, occ16);
     if (small_kmax(K) == 9)
         routing_small_fwd_kernel<9><<<grid, kST, 0, st>>>(xrot, lrfs, act, Wc, bc, alpha, beta, pose, agreement,
                                                           poses_all, stats, BP, K, O, T);
@@ -310,7 +320,9 @@ extern "C" int qec_routing_small_bwd(const float* xrot, const float* lrfs, const
     QEC_CHECK_ARG(BP > 0, 15);
     QEC_CHECK_ARG(qec_routing_small_supported(K, 1, O, T), 16);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const dim3 grid = small_grid(BP, O);
+    static int occ9 = -1, occ16 = -1;
+    const dim3 grid = (small_kmax(K) == 9) ? small_grid(routing_small_bwd_kernel<9>, BP, O, occ9)
+                                           : small_grid(routing_small_bwd_kernel<16>, BP, O, occ16);
     if (small_kmax(K) == 9)
         routing_small_bwd_kernel<9><<<grid, kST, 0, st>>>(xrot, lrfs, act, Wc, bc, alpha, beta, poses_all, stats,
                                                           g_pose, g_agreement, g_Wc, g_bc, g_alpha_beta, BP, K, O, T);
