@@ -156,6 +156,18 @@ int qec_routing_fused_bwd_split(const float* t_oqi, const float* lrfs, const flo
                                 const float* g_agreement, float* g_toqi_hi, unsigned short* g_toqi_lo, float* g_lrfs,
                                 float* g_act, float* g_alpha_beta, int BP, int K, int I, int O, int T, void* stream);
 
+/* Deterministic K-nearest-neighbour indices of the patch centres (on-device
+ * counterpart of the neighbourhood index files the reference's loader consumes,
+ * my_dataloader/modelnet_with_lrf_sample_index_loader.py:130-160, produced offline by
+ * my_dataloader/gen_downsample_m40.py:86-150).  d = ((cx-x)^2 + (cy-y)^2) + (cz-z)^2 with every
+ * operation rounded to float32 separately; neighbours sorted by (d, index) ascending -> bit-exact
+ * against the float32 CPU statement oracle/qec_oracle.py:knn_indices.  points [B,N,3]; centres given
+ * either as point indices (centre_idx [B,P] int64) or as coordinates (centres [B,P,3]), exactly one
+ * non-null; idx_out [B,P,K] int64 (-1 where N < K); K <= 64.  err: device int set to 1 if a centre
+ * index is outside [0, N).  The output feeds qec_gather. */
+int qec_knn(const float* points, const float* centres, const long long* centre_idx, long long* idx_out, int* err,
+            int B, int N, int P, int K, void* stream);
+
 /* Operand preparation for the quater_gen2 GEMMs on the tensor cores at FP32 accuracy ("3xTF32";
  * reference: nn.Linear in models/qec_module.py:124 and its autograd backward, FP32 cuBLAS SGEMM).
  * qec_split_operand: src [R, C] (+ one extra column when add_col: extra[R] if given, else

@@ -333,6 +333,36 @@ def neighbour_gather(point_set, lrf_set, idx, wrong_ids=None):
 # --------------------------------------------------------------------------
 
 
+def knn_indices(points, K, centre_idx=None, centres=None):
+    """K nearest neighbours of the patch centres, plain float32 statement (the checker of qec_knn).
+    The reference has no neighbour search of its own: its neighbourhoods are read from index files
+    written offline by my_dataloader/gen_downsample_m40.py:86-150 (scipy cdist + greedy grouping) and
+    consumed by my_dataloader/modelnet_with_lrf_sample_index_loader.py:130-160.  SURVEY.md 8 f.2 fixes the
+    on-device contract instead: squared distances in float32 with every operation rounded separately,
+    d = ((cx-x)^2 + (cy-y)^2) + (cz-z)^2, neighbours ordered by (d, point index) -- a stable sort.
+    points [B,N,3]; centre_idx [B,P] int64 or centres [B,P,3] -> idx [B,P,K] int64 (-1 where N < K)."""
+    import numpy as np
+
+    pts = points.detach().cpu().numpy().astype(np.float32)
+    B, N, _ = pts.shape
+    if centre_idx is not None:
+        ci = centre_idx.detach().cpu().numpy()
+        c = np.stack([pts[b][ci[b]] for b in range(B)], 0)
+    else:
+        c = centres.detach().cpu().numpy().astype(np.float32)
+    P = c.shape[1]
+    out = np.full((B, P, K), -1, np.int64)
+    for b in range(B):
+        dx = (c[b, :, None, 0] - pts[b, None, :, 0]).astype(np.float32)
+        dy = (c[b, :, None, 1] - pts[b, None, :, 1]).astype(np.float32)
+        dz = (c[b, :, None, 2] - pts[b, None, :, 2]).astype(np.float32)
+        d = ((dx * dx).astype(np.float32) + (dy * dy).astype(np.float32)).astype(np.float32)
+        d = (d + (dz * dz).astype(np.float32)).astype(np.float32)
+        order = np.argsort(d, axis=1, kind="stable")[:, :K]
+        out[b, :, : order.shape[1]] = order
+    return torch.from_numpy(out)
+
+
 def _small_rotation(rotvec):
     ang = rotvec.norm(dim=-1, keepdim=True)
     half = 0.5 * ang

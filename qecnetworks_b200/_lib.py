@@ -36,6 +36,7 @@ SIGNATURES = {
     "qec_symeig4_fwd": ([_P, _P, _P, _P, _LL, _P], 1),
     "qec_symeig4_bwd": ([_P, _P, _P, _P, _P, _LL, _I, _P], 1),
     "qec_gather": ([_P] * 9 + [_I, _I, _I, _I, _I, _P], 1),
+    "qec_knn": ([_P] * 5 + [_I, _I, _I, _I, _P], 1),
     "qec_split_operand": ([_P, _P, _F, _P, _P, _P, _LL, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], 1),
     "qec_fold_chunks": ([_P, _P, _P, _P, _P, _I, _LL, _I, _I, _I, _P], 1),
     "qec_spread_loss": ([_P, _P, _F, _P, _P, _P, _P, _I, _I, _P], 2),

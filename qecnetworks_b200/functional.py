@@ -338,6 +338,30 @@ def routing(votes_, activation, alpha, beta, num_iterations):
     return Routing.apply(votes_, activation, alpha, beta, num_iterations)
 
 
+def knn_indices(points, K, centre_idx=None, centres=None):
+    """K nearest neighbours of P centres among the N points of each sample, on the device (qec_knn):
+    points [B,N,3] float32; centres as point indices centre_idx [B,P] int64 or coordinates centres [B,P,3].
+    -> idx [B,P,K] int64 sorted by (squared distance, point index), bit-exact against
+    oracle.qec_oracle.knn_indices; err [1] int32 (1 = a centre index was out of range).  The result is
+    what neighbour_gather consumes."""
+    B, N, _ = points.shape
+    points = _check(points, "points", (B, N, 3))
+    if (centre_idx is None) == (centres is None):
+        raise ValueError("give exactly one of centre_idx / centres")
+    if centre_idx is not None:
+        if not centre_idx.is_cuda or centre_idx.dtype != torch.int64:
+            raise TypeError("centre_idx must be a CUDA int64 tensor")
+        centre_idx = centre_idx.contiguous()
+        P = centre_idx.shape[1]
+    else:
+        P = centres.shape[1]
+        centres = _check(centres, "centres", (B, P, 3))
+    idx = torch.empty(B, P, int(K), device=points.device, dtype=torch.int64)
+    err = torch.zeros(1, device=points.device, dtype=torch.int32)
+    call("qec_knn", ptr(points), ptr(centres), ptr(centre_idx), ptr(idx), ptr(err), B, N, P, int(K), _stream())
+    return idx, err
+
+
 def neighbour_gather(point_set, lrf_set, idx, wrong_ids=None, wrong_count=None):
     """Batched loader gather on the device (reference
     my_dataloader/modelnet_with_lrf_sample_index_loader.py:130-160).

@@ -259,6 +259,38 @@ def test_gather_bit_exact():
     assert int(err.item()) == 1
 
 
+@pytest.mark.parametrize("B,N,P,K", [(3, 1024, 256, 9), (2, 2048, 64, 64), (2, 37, 5, 9), (1, 5, 3, 9), (2, 300, 16, 1)])
+def test_knn_indices_bit_exact(B, N, P, K):
+    """qec_knn against the float32 CPU statement: indices bit-exact, incl. exact distance ties (points on
+    a grid, duplicated points), fewer points than K, and centres given as coordinates"""
+    from qecnetworks_b200 import functional as QF
+
+    dev = cuda()
+    gen = torch.Generator().manual_seed(N * 7 + K)
+    pts = torch.randn(B, N, 3, generator=gen)
+    pts[0] = torch.round(pts[0] * 4) / 4          # a coarse grid: many exact ties
+    if N > 8:
+        pts[-1, N // 2:N // 2 + 4] = pts[-1, 0]    # duplicates of one point
+    ci = torch.stack([torch.randperm(N, generator=gen)[:P] if N >= P else torch.randint(0, N, (P,), generator=gen)
+                      for _ in range(B)])
+    ref = orc.knn_indices(pts, K, centre_idx=ci)
+    idx, err = QF.knn_indices(pts.to(dev), K, centre_idx=ci.to(dev))
+    assert int(err.item()) == 0
+    assert torch.equal(idx.cpu(), ref)
+    cen = torch.randn(B, P, 3, generator=gen)
+    ref2 = orc.knn_indices(pts, K, centres=cen)
+    idx2, _ = QF.knn_indices(pts.to(dev), K, centres=cen.to(dev))
+    assert torch.equal(idx2.cpu(), ref2)
+    bad = ci.clone()
+    bad[0, 0] = N + 1
+    _, err = QF.knn_indices(pts.to(dev), K, centre_idx=bad.to(dev))
+    assert int(err.item()) == 1
+    if N >= K:   # the indices feed the loader gather: neighbourhoods of the centres, centre first
+        ps, ls = pts.to(dev), torch.randn(B, N, 4, generator=gen).to(dev)
+        gp, gl, ga, gerr = QF.neighbour_gather(ps, ls, idx)
+        assert int(gerr.item()) == 0 and gp.shape == (B, P, K, 3)
+
+
 # ---------------------------------------------------------------- fused cluster-resident routing
 def _oqi_perm(I, O):
     o = torch.arange(O).view(O, 1, 1)

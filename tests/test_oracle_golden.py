@@ -148,3 +148,23 @@ def test_gather_golden():
         assert torch.equal(p, g["s%d.points" % n])
         assert torch.equal(l, g["s%d.lrfs" % n])
         assert torch.equal(a, g["s%d.act" % n])
+
+
+def test_knn_oracle_properties():
+    """oracle knn_indices (the checker of qec_knn): first neighbour of a centre that is a point is a point
+    at distance 0, distances are non-decreasing, ties go to the smaller index, -1 padding when N < K"""
+    g = torch.Generator().manual_seed(3)
+    pts = torch.round(torch.randn(2, 50, 3, generator=g) * 2) / 2
+    ci = torch.stack([torch.randperm(50, generator=g)[:7] for _ in range(2)])
+    idx = orc.knn_indices(pts, 9, centre_idx=ci)
+    assert idx.shape == (2, 7, 9)
+    for b in range(2):
+        for p in range(7):
+            c = pts[b, ci[b, p]]
+            d = ((pts[b, idx[b, p]] - c) ** 2).sum(-1)
+            assert float(d[0]) == 0.0
+            assert bool((d[1:] >= d[:-1]).all())
+            ties = (d[1:] == d[:-1])
+            assert bool((idx[b, p, 1:][ties] > idx[b, p, :-1][ties]).all())
+    few = orc.knn_indices(pts[:, :4], 9, centre_idx=ci % 4)
+    assert bool((few[..., 4:] == -1).all()) and bool((few[..., :4] >= 0).all())
