@@ -333,6 +333,27 @@ def neighbour_gather(point_set, lrf_set, idx, wrong_ids=None):
 # --------------------------------------------------------------------------
 
 
+def ave_pose(pose):
+    """test_rot_sia.py:16-29, batched restatement: top eigenvector of the mean outer product of the poses
+    whose components do not sum to zero, sign-fixed.  pose [B,n,4] -> [B,4]"""
+    out = []
+    for b in range(pose.shape[0]):
+        keep = pose[b].sum(-1) != 0
+        q = pose[b][keep]
+        M = (q.unsqueeze(2) * q.unsqueeze(1)).mean(0)
+        w, V = torch.linalg.eigh(M, UPLO="U")
+        v = V[:, 3]
+        out.append(v * torch.sign(v[0]))
+    return torch.stack(out, 0)
+
+
+def q_distance(pose1, pose2):
+    """test_rot_sia.py:32-41"""
+    p1 = pose1 * torch.sign(pose1[..., :1])
+    p2 = pose2 * torch.sign(pose2[..., :1])
+    return 2.0 * torch.acos((p1 * p2).sum(-1).abs().clamp(max=1.0)) / math.pi
+
+
 def knn_indices(points, K, centre_idx=None, centres=None):
     """K nearest neighbours of the patch centres, plain float32 statement (the checker of qec_knn).
     The reference has no neighbour search of its own: its neighbourhoods are read from index files

@@ -8,8 +8,9 @@ from .qec_module import QecModule
 from .qec_net import QecNet, QecSiaNet
 from .symeig import symeig
 from . import functional
+from . import eval_ops
 
-__all__ = ["QecModule", "QecNet", "QecSiaNet", "symeig", "functional", "kernel_launches", "library_path"]
+__all__ = ["QecModule", "QecNet", "QecSiaNet", "symeig", "functional", "eval_ops", "kernel_launches", "library_path"]
 
 
 def kernel_launches():

@@ -198,3 +198,28 @@ def test_stress_sweep_corners(K, O, T):
         pose, agr = mod(points.to(dev), lrfs.unsqueeze(-2).to(dev), act.unsqueeze(-1).to(dev))
     assert quat_err(pose.cpu(), pose_ref) < TOL
     assert max_err(agr.cpu(), agr_ref) < TOL
+
+
+def test_eval_ops_vs_oracle():
+    """evaluation-side ops of test_rot_sia.py (ave_pose, q_distance, relative pose) batched on the device
+    against their restatement (float64), incl. zeroed poses and the reference's sum-to-zero mask"""
+    import qecnetworks_b200 as qb
+    from qecnetworks_b200 import eval_ops as E
+
+    dev = cuda()
+    gen = torch.Generator().manual_seed(17)
+    base = torch.randn(6, 1, 4, generator=gen)
+    q = base + 0.3 * torch.randn(6, 300, 4, generator=gen)
+    q = q / q.norm(dim=-1, keepdim=True)
+    q = q * torch.where(q[..., :1] < 0, -1.0, 1.0)
+    q[:, ::7] = 0                                        # invalid LRFs
+    q[0, 1] = torch.tensor([0.5, -0.5, 0.5, -0.5])      # non-zero but excluded by the reference's mask
+    ref = orc.ave_pose(q.double())
+    got = E.ave_pose(q.to(dev))
+    assert quat_err(got.cpu(), ref) < 1e-5
+    assert float(got[:, 0].min()) >= 0.0
+    a, b = q[:, 3].to(dev), q[:, 5].to(dev)
+    assert max_err(E.q_distance(a, b).cpu(), orc.q_distance(q[:, 3].double(), q[:, 5].double())) < 1e-5
+    rel = E.relative_pose(a, b)
+    assert max_err(rel.cpu(), orc.ham(orc.conj(q[:, 3]), q[:, 5])) < 1e-6
+    assert qb.eval_ops is E
