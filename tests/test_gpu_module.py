@@ -223,3 +223,38 @@ def test_eval_ops_vs_oracle():
     rel = E.relative_pose(a, b)
     assert max_err(rel.cpu(), orc.ham(orc.conj(q[:, 3]), q[:, 5])) < 1e-6
     assert qb.eval_ops is E
+
+
+def test_training_trajectory_matches_oracle():
+    """eight Adam steps of QecNet (C=16, 5 classes, B=2) on the device and in the float64 oracle from the
+    same initialisation and batch: the loss trajectories agree step by step and the loss goes down --
+    forward, backward and the update loop end to end"""
+    import qecnetworks_b200 as qb
+
+    dev = cuda()
+    params = orc.init_net_params(16, 5, seed=2)
+    points, lrfs, act, labels = orc.synthetic_batch(2, ncls=5, seed=8)
+    p64 = {k: v.double().clone().requires_grad_(True) for k, v in params.items()}
+    net = qb.QecNet(2048, 16, 5, 3)
+    net.load_state_dict(params)
+    net = net.to(dev)
+    keys = [k for k, _ in net.named_parameters()]
+    opt_d = torch.optim.Adam(net.parameters(), lr=1e-3)
+    opt_o = torch.optim.Adam([p64[k] for k in keys], lr=1e-3)
+    pd, ld, ad, yd = points.to(dev), lrfs.to(dev), act.to(dev), labels.to(dev)
+    got, ref = [], []
+    for _ in range(8):
+        opt_d.zero_grad()
+        _, a = net(pd, ld, ad, None)
+        loss = net.spread_loss(a, yd)
+        loss.backward()
+        opt_d.step()
+        got.append(float(loss.detach()))
+        opt_o.zero_grad()
+        _, a_ref = orc.qec_net_forward(p64, points.double(), lrfs.double(), act.double(), 3)
+        loss_ref = orc.spread_loss(a_ref, labels)
+        loss_ref.backward()
+        opt_o.step()
+        ref.append(float(loss_ref.detach()))
+    assert max(abs(g - r) for g, r in zip(got, ref)) < 1e-4 * max(1.0, max(ref)), (got, ref)
+    assert got[-1] < got[0]
