@@ -25,39 +25,43 @@ __device__ __forceinline__ float operand_at(const float* __restrict__ src, const
     return 0.f;
 }
 
-// one thread per output element: out_f32 [R, WT] = nblk blocks of stride BS (block j = hi or lo part of
-// the Kc = C + add_col real columns), zero elsewhere; then out_bf16 [R, WB] = hi part, zero-padded
+// one warp per output row (lanes run along the columns: coalesced stores, the permutation entry and the
+// source row are read once per warp): out_f32 [R, WT] = nblk blocks of stride BS (block j = hi or lo
+// part of the Kc = C + add_col real columns), zero elsewhere; out_bf16 [R, WB] = hi part, zero-padded
 __global__ void __launch_bounds__(256)
     split_operand_kernel(const float* __restrict__ src, const float* __restrict__ extra, float extra_const,
                          const long long* __restrict__ perm, float* __restrict__ out_f32,
                          unsigned short* __restrict__ out_bf16, long long R, int C, int add_col, int BS, int WT, int WB,
                          int b0, int b1, int b2, int nblk) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= R) return;
+    const int lane = threadIdx.x & 31;
     const int Kc = C + (add_col ? 1 : 0);
-    const long long n32 = out_f32 ? R * WT : 0;
-    if (idx < n32) {
-        const long long r = idx / WT;
-        const int col = (int)(idx - r * WT);
-        const int j = col / BS, c = col - j * BS;
-        float o = 0.f;
-        if (j < nblk && c < Kc) {
-            const float v = operand_at(src, extra, extra_const, perm ? perm[r] : r, c, C, add_col);
-            const float hi = tf32_rn(v);
-            const int kind = (j == 0) ? b0 : ((j == 1) ? b1 : b2);
-            o = (kind == 1) ? hi : tf32_rn(v - hi);
+    const long long sr = perm ? perm[r] : r;
+    if (out_f32) {
+        float* o = out_f32 + r * WT;
+        for (int c = lane; c < BS; c += 32) {  // the same source column feeds block j at column j * BS + c
+            float hi = 0.f, lo = 0.f;
+            if (c < Kc) {
+                const float v = operand_at(src, extra, extra_const, sr, c, C, add_col);
+                hi = tf32_rn(v);
+                lo = tf32_rn(v - hi);
+            }
+            if (nblk > 0) o[c] = (b0 == 1) ? hi : lo;
+            if (nblk > 1) o[BS + c] = (b1 == 1) ? hi : lo;
+            if (nblk > 2) o[2 * BS + c] = (b2 == 1) ? hi : lo;
         }
-        out_f32[idx] = o;
-        return;
+        for (int c = nblk * BS + lane; c < WT; c += 32) o[c] = 0.f;  // tail padding
     }
-    const long long k = idx - n32;
-    if (out_bf16 && k < R * WB) {
-        const long long r = k / WB;
-        const int c = (int)(k - r * WB);
-        float hi = 0.f;
-        if (c < Kc) hi = tf32_rn(operand_at(src, extra, extra_const, perm ? perm[r] : r, c, C, add_col));
-        unsigned short h;
-        asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(h) : "f"(hi));
-        out_bf16[k] = h;
+    if (out_bf16) {
+        unsigned short* o = out_bf16 + r * WB;
+        for (int c = lane; c < WB; c += 32) {
+            float hi = 0.f;
+            if (c < Kc) hi = tf32_rn(operand_at(src, extra, extra_const, sr, c, C, add_col));
+            unsigned short h;
+            asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(h) : "f"(hi));
+            o[c] = h;
+        }
     }
 }
 
@@ -70,8 +74,21 @@ __global__ void __launch_bounds__(256)
     if (idx >= R * K) return;
     const long long r = idx / K;
     const int c = (int)(idx - r * K);
+    // the chunks are summed in ascending order; four are in flight at a time (the loads, not the adds,
+    // are what this loop waits for)
     float acc = 0.f;
-    for (int s = 0; s < S; ++s) {
+    int s = 0;
+    for (; s + 4 <= S; s += 4) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float* pa = a + ((long long)(s + u) * R + r) * (2 * KP);
+            const float* pb = b + ((long long)(s + u) * R + r) * KP;
+            v[u] = (__ldg(pa + c) + __ldg(pa + KP + c)) + __ldg(pb + c);
+        }
+        acc += v[0]; acc += v[1]; acc += v[2]; acc += v[3];
+    }
+    for (; s < S; ++s) {
         const float* pa = a + ((long long)s * R + r) * (2 * KP);
         const float* pb = b + ((long long)s * R + r) * KP;
         acc += (__ldg(pa + c) + __ldg(pa + KP + c)) + __ldg(pb + c);
@@ -98,8 +115,7 @@ extern "C" int qec_split_operand(const float* src, const float* extra, float ext
     QEC_CHECK_ARG(nblk >= 0 && nblk <= 3, 16);
     if (out_f32) QEC_CHECK_ARG(BS >= Kc && WT >= nblk * BS, 10);
     if (out_bf16) QEC_CHECK_ARG(WB >= Kc, 12);
-    const long long n = (out_f32 ? R * WT : 0) + (out_bf16 ? R * WB : 0);
-    const unsigned grid = (unsigned)((n + 255) / 256);
+    const unsigned grid = (unsigned)((R + 7) / 8);  // 8 warps = 8 rows per CTA
     qec::split_operand_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         src, extra, extra_const, perm, out_f32, out_bf16, R, C, add_col, BS, WT, WB, blk0, blk1, blk2, nblk);
     return qec::launch_status();
