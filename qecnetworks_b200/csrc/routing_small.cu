@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kST)
         Quat p;
         for (int t = 0;; ++t) {
             const Sym4 m = acc_to_sym(acc, 1.f / fmaxf(acc[10], 1e-12f));
-            p = qfix(top_eigvec_weighted(m, acc[12] != acc[10], WarpDone()));
+            p = qfix(top_eigvec_weighted2(m, acc[12] != acc[10], WarpDone()));
             if (!valid) p = qmake(0.f, 0.f, 0.f, 0.f);
             if (active) stq(poses_all + ((size_t)t * Nc + c) * 4, p);
             if (t == T - 1) break;
