@@ -97,6 +97,9 @@ def run_reference(a):
 
 # ------------------------------------------------------------------ clocks sampler
 class ClockSampler:
+    """SM clock, power and throttle reasons sampled DURING the timed region: NVML from a thread every 2 ms
+    (the regions last tens of milliseconds; `nvidia-smi -lms` cannot sample faster than ~20 ms), with
+    nvidia-smi as the fallback when the NVML binding is missing."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
@@ -105,8 +108,35 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.samples = []   # (sm_mhz, sm_max_mhz, power_w, reasons bitmask)
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.nvml = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber the devices: address the GPU by its PCI bus id
+            import torch
+            bus = torch.cuda.get_device_properties(self.index).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(self.index), "pci_bus_id") else None
+            h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(hi).bus == bus:
+                        h = hi
+                        break
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml = (pynvml, h)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
@@ -116,11 +146,39 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        pynvml, h = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                rs = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.samples.append((sm, self.sm_max, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            pynvml, _ = self.nvml
+            self.stop_flag.set()
+            self.thread.join(timeout=1)
+            sm = sorted(s[0] for s in self.samples)
+            bits = 0
+            for s in self.samples:
+                bits |= s[3]
+            names = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
+            reasons = sorted(n for n, m in names.items() if bits & m)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max if sm else None,
+                    "power_w_max": max((s[2] for s in self.samples), default=None), "samples": len(sm),
+                    "reasons": reasons, "source": "nvml, 2 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -145,7 +203,8 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": "nvidia-smi -lms 20"}
 
 
 # ------------------------------------------------------------------ roofline accounting
