@@ -637,8 +637,8 @@ __device__ __forceinline__ void complete_levels2(const Bwd2Caps& C, const Quat2&
     }
 }
 
-// element offsets (32-bit; qec_routing_fused_packed_supported bounds the tensor sizes) instead of
-// six 64-bit pointers: the bases stay in the kernel-parameter bank
+// element offsets instead of six 64-bit pointers per capsule: the bases stay in the kernel-parameter bank
+// (offA and the in-block walker are 32-bit: qec_routing_fused_packed_supported bounds one bp block)
 struct Bwd2Geom {
     const float* act;
     const float* lrfs;
@@ -648,7 +648,7 @@ struct Bwd2Geom {
     float* g_lrfs;   // nullable
     float* g_act;    // nullable: no activation gradient -> only the top level is processed
     unsigned offA;   // bp * J + j_begin: first vote of this CTA's slice in act / g_act (x4 in lrfs / g_lrfs)
-    unsigned offT;   // bp * K * trow + o * 4I: the capsule's block in t_oqi / g_toqi
+    size_t offT;     // bp * K * trow + o * 4I: the capsule's block in t_oqi / g_toqi (64-bit: > 2^32 elements at large B)
     int I, dko, di, wrap;  // pair walker: per slot j += 2 * kPT
 };
 
@@ -666,11 +666,11 @@ struct OffWalk {
 };
 
 template <bool FULL>
-__device__ __forceinline__ void prefetch_walk(const Bwd2Geom& B, unsigned offT_next, OffWalk& w, float4* sA, float4* sB,
+__device__ __forceinline__ void prefetch_walk(const Bwd2Geom& B, size_t offT_next, OffWalk& w, float4* sA, float4* sB,
                                               int np, int m) {
     const int ps = threadIdx.x + m * kPT;
     if (FULL || ps < np) {
-        const float* tp = B.t_oqi + (size_t)(offT_next + (unsigned)w.off);
+        const float* tp = B.t_oqi + (offT_next + (size_t)w.off);
         float* a = reinterpret_cast<float*>(sA + ps);
         float* b = reinterpret_cast<float*>(sB + ps);
         cp_async8(a, tp);
@@ -687,7 +687,7 @@ __device__ __forceinline__ void prefetch_walk(const Bwd2Geom& B, unsigned offT_n
 // which keeps both under the 128-register budget of two CTAs per SM.
 template <int T, bool FULL, bool PREFETCH>
 __device__ __forceinline__ void bwd2_grad_pass(int np, const Bwd2Geom& B, const Bwd2Caps& C, OffWalk w0, float4* sA,
-                                               float4* sB, unsigned offT_next) {
+                                               float4* sB, size_t offT_next) {
     constexpr int TT = T - 1;
     float2* som0 = reinterpret_cast<float2*>(sB + kNpMax);
     float2* som1 = som0 + kNpMax;
@@ -697,7 +697,7 @@ __device__ __forceinline__ void bwd2_grad_pass(int np, const Bwd2Geom& B, const 
         const int ps = threadIdx.x + m * kPT;
         if (FULL || ps < np) {
             // issued first: the level walk below hides their latency
-            const float* tp = B.t_oqi + (size_t)(B.offT + (unsigned)w.off);
+            const float* tp = B.t_oqi + (B.offT + (size_t)w.off);
             Quat2 traw;
             traw.w = ldg_f2(tp); traw.x = ldg_f2(tp + B.I); traw.y = ldg_f2(tp + 2 * B.I); traw.z = ldg_f2(tp + 3 * B.I);
             const float* lp = B.lrfs + ((size_t)B.offA + 2 * ps) * 4;
@@ -716,12 +716,12 @@ __device__ __forceinline__ void bwd2_grad_pass(int np, const Bwd2Geom& B, const 
             const VotePair vp = make_vote2<true>(lrf, traw);
             Quat2 gt, gq;
             vote_bwd2(lrf, vp, gv, gt, gq);
-            float* gp = B.g_toqi + (size_t)(B.offT + (unsigned)w.off);
+            float* gp = B.g_toqi + (B.offT + (size_t)w.off);
             if (B.g_lo != nullptr) {
                 // pre-split for the tensor-core GEMMs that consume it (quater_gen2's backward at FP32
                 // accuracy): hi on the TF32 grid (an exact tensor-core input); the remainder g - hi (exact in
                 // FP32, at most 2^-11 |g|) only has to carry ~11 more bits and travels as BF16
-                unsigned* gq2 = reinterpret_cast<unsigned*>(B.g_lo + (size_t)(B.offT + (unsigned)w.off));
+                unsigned* gq2 = reinterpret_cast<unsigned*>(B.g_lo + (B.offT + (size_t)w.off));
                 const f2 hw = tf32_round2(gt.w), hx = tf32_round2(gt.x), hy = tf32_round2(gt.y), hz = tf32_round2(gt.z);
                 const int Ih = B.I >> 1;  // pair stride in 32-bit words
                 gq2[0] = bf16x2(fma2(hw, bc(-1.f), gt.w));
@@ -748,7 +748,7 @@ __device__ __forceinline__ void bwd2_grad_pass(int np, const Bwd2Geom& B, const 
 // ---- sweep that completes level TT (u^TT known) and accumulates level TT-1 (chain only)
 template <int T, int TT, bool FULL, bool PREFETCH>
 __device__ __forceinline__ void bwd2_acc_sweep(int np, const Bwd2Geom& B, const Bwd2Caps& C, OffWalk w0, float4* sA,
-                                               float4* sB, unsigned offT_next, float (&acc)[15]) {
+                                               float4* sB, size_t offT_next, float (&acc)[15]) {
     float2* som0 = reinterpret_cast<float2*>(sB + kNpMax);
     float2* som1 = som0 + kNpMax;
     f2 a2[14];
@@ -904,11 +904,11 @@ __global__ void __launch_bounds__(kPT, 2)
     auto offT_of = [&](long long c) {
         const long long bp = c / O;
         const int o = (int)(c - bp * O);
-        return (unsigned)bp * (unsigned)K * trow + (unsigned)o * 4u * (unsigned)I;
+        return (size_t)bp * K * trow + (size_t)o * 4 * I;
     };
     if (cid < Nc) {
         OffWalk w = w0;
-        const unsigned o0 = offT_of(cid);
+        const size_t o0 = offT_of(cid);
 #pragma unroll
         for (int m = 0; m < kPairs; ++m) prefetch_walk<FULL>(B, o0, w, sA, sB, np, m);
     }
@@ -919,7 +919,7 @@ __global__ void __launch_bounds__(kPT, 2)
         B.offT = offT_of(c);
         const long long cn = c + ncl;
         const bool more = cn < Nc;
-        const unsigned offT_next = more ? offT_of(cn) : 0u;
+        const size_t offT_next = more ? offT_of(cn) : (size_t)0;
         // Per-capsule state lives in memory between sweeps, not in registers: the poses are re-read from
         // poses_all (L2) and the adjoint vectors u^t / 1/S^t from a 32-float shared array, so that each
         // sweep only keeps what it uses live (the 28 registers of the full state made the sweeps spill).
