@@ -111,6 +111,124 @@ __global__ void __launch_bounds__(kLT)
     }
 }
 
+
+// ------------------------------------------------------------------------------------
+// Tile variants for wide layers (I >= 32, K > 32: pool2, K = 256 neighbours x I = 128 channels).
+// The warp-per-(bp,i) kernels above walk k with lanes 2 KB apart: every load is its own sector.  Here a
+// CTA owns 32 consecutive channels i of one bp: lane = channel (a warp reads 512 contiguous bytes of
+// lrfs per k), warp = slice of k; the kTW partial sums per channel meet in shared memory, warp 0 solves
+// the 32 channels, and (backward) every thread writes dL/dlrfs for the (k, i) it read.
+// ------------------------------------------------------------------------------------
+constexpr int kTW = 16;  // warps per CTA = slices of k
+
+__global__ void __launch_bounds__(kTW * 32)
+    lrf_mean_fwd_tile_kernel(const float* __restrict__ lrfs, const float* __restrict__ act, float* __restrict__ mean,
+                             int K, int I) {
+    __shared__ float part[kTW][11][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tiles = (I + 31) / 32;
+    const long long bp = blockIdx.x / tiles;
+    const int i = (int)(blockIdx.x - bp * tiles) * 32 + lane;
+    const bool live = i < I;
+    float acc[11];  // M (10), number of active neighbours
+    zero_acc(acc);
+    if (live) {
+#pragma unroll 4
+        for (int k = warp; k < K; k += kTW) {
+            const size_t e = ((size_t)bp * K + k) * I + i;
+            const Quat q = ldq_nc(lrfs + e * 4);
+            acc_rank1(acc, 1.f, q);
+            acc[10] += (__ldg(act + e) != 0.f) ? 1.f : 0.f;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 11; ++j) part[warp][j][lane] = acc[j];
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int j = 0; j < 11; ++j) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < kTW; ++w) t += part[w][j][lane];  // fixed order
+            acc[j] = t;
+        }
+        const Sym4 m = acc_to_sym(acc, 1.f / (float)K);
+        Quat p = qfix(top_eigvec_psd(m, WarpDone()));  // (1/K) sum q q^T is positive semi-definite
+        if (!(acc[10] > 0.f)) p = qmake(0.f, 0.f, 0.f, 0.f);
+        if (live) stq(mean + ((size_t)bp * I + i) * 4, p);
+    }
+}
+
+__global__ void __launch_bounds__(kTW * 32)
+    lrf_mean_bwd_tile_kernel(const float* __restrict__ lrfs, const float* __restrict__ points,
+                             const float* __restrict__ mean, const float* __restrict__ g_xrot,
+                             const float* __restrict__ g_mean, float* __restrict__ g_lrfs, float* g_points, int K,
+                             int I) {
+    __shared__ float part[kTW][14][32];
+    __shared__ float us[4][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tiles = (I + 31) / 32;
+    const long long bp = blockIdx.x / tiles;
+    const int i = (int)(blockIdx.x - bp * tiles) * 32 + lane;
+    const bool live = i < I;
+    const Quat m = live ? ldq_nc(mean + ((size_t)bp * I + i) * 4) : qmake(0.f, 0.f, 0.f, 0.f);
+    const Quat cj = qconj(m);
+    float acc[14];  // g_conj (4), M (10)
+    zero_acc(acc);
+    if (live) {
+#pragma unroll 2
+        for (int k = warp; k < K; k += kTW) {
+            const size_t bpk = (size_t)bp * K + k;
+            const size_t e = bpk * I + i;
+            const Quat q = ldq_nc(lrfs + e * 4);
+            const float* pp = points + bpk * 3;
+            const float* gp = g_xrot + e * 3;
+            Quat gq;
+            Vec3 gv;
+            qrotv_bwd(cj, vmake(__ldg(pp), __ldg(pp + 1), __ldg(pp + 2)), vmake(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2)),
+                      gq, gv);
+            acc[0] += gq.w; acc[1] += gq.x; acc[2] += gq.y; acc[3] += gq.z;
+            acc_rank1(acc + 4, 1.f, q);
+            if (g_points != nullptr) {
+                atomicAdd(g_points + bpk * 3 + 0, gv.x);
+                atomicAdd(g_points + bpk * 3 + 1, gv.y);
+                atomicAdd(g_points + bpk * 3 + 2, gv.z);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 14; ++j) part[warp][j][lane] = acc[j];
+    __syncthreads();
+    const float rk = 1.f / (float)K;
+    if (warp == 0) {
+#pragma unroll
+        for (int j = 0; j < 14; ++j) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < kTW; ++w) t += part[w][j][lane];  // fixed order
+            acc[j] = t;
+        }
+        // c = conj(m): dL/dm = conj(dL/dc)
+        Quat gm = qmake(acc[0], -acc[1], -acc[2], -acc[3]);
+        if (g_mean != nullptr && live) gm = qadd(gm, ldq_nc(g_mean + ((size_t)bp * I + i) * 4));
+        const Sym4 M = acc_to_sym(acc + 4, rk);
+        const float lam = qdot(m, sym_mul(M, m));
+        Quat u = top_eigvec_adjoint(M, m, lam, gm);
+        if (!(qdot(m, m) > 0.5f)) u = qmake(0.f, 0.f, 0.f, 0.f);
+        us[0][lane] = u.w; us[1][lane] = u.x; us[2][lane] = u.y; us[3][lane] = u.z;
+    }
+    __syncthreads();
+    if (!live) return;
+    const Quat u = qmake(us[0][lane], us[1][lane], us[2][lane], us[3][lane]);
+    for (int k = warp; k < K; k += kTW) {
+        const size_t e = ((size_t)bp * K + k) * I + i;
+        const Quat q = ldq_nc(lrfs + e * 4);
+        // d/dq of (1/K) q^T (sym(u m^T)) q ... = (1/K) (u <m,q> + m <u,q>)
+        const Quat g = qfma(rk * qdot(m, q), u, qscale(m, rk * qdot(u, q)));
+        stq(g_lrfs + e * 4, g);
+    }
+}
+
 }  // namespace qec
 
 using namespace qec;
@@ -128,6 +246,9 @@ extern "C" int qec_lrf_mean_fwd(const float* lrfs, const float* act, const float
     if (K <= 32) {
         const long long blocks = (Ncap + kLT - 1) / kLT;
         lrf_mean_fwd_kernel<1><<<(unsigned)blocks, kLT, 0, st>>>(lrfs, act, mean, Ncap, K, I);
+    } else if (I >= 32) {
+        const long long blocks = (long long)BP * ((I + 31) / 32);
+        lrf_mean_fwd_tile_kernel<<<(unsigned)blocks, kTW * 32, 0, st>>>(lrfs, act, mean, K, I);
     } else {
         const long long blocks = (Ncap * 32 + kLT - 1) / kLT;
         lrf_mean_fwd_kernel<32><<<(unsigned)blocks, kLT, 0, st>>>(lrfs, act, mean, Ncap, K, I);
@@ -157,6 +278,10 @@ extern "C" int qec_lrf_mean_bwd(const float* lrfs, const float* points, const fl
         const long long blocks = (Ncap + kLT - 1) / kLT;
         lrf_mean_bwd_kernel<1><<<(unsigned)blocks, kLT, 0, st>>>(lrfs, points, mean, g_xrot, g_mean, g_lrfs,
                                                                  g_points, Ncap, K, I);
+    } else if (I >= 32) {
+        const long long blocks = (long long)BP * ((I + 31) / 32);
+        lrf_mean_bwd_tile_kernel<<<(unsigned)blocks, kTW * 32, 0, st>>>(lrfs, points, mean, g_xrot, g_mean, g_lrfs,
+                                                                          g_points, K, I);
     } else {
         const long long blocks = (Ncap * 32 + kLT - 1) / kLT;
         lrf_mean_bwd_kernel<32><<<(unsigned)blocks, kLT, 0, st>>>(lrfs, points, mean, g_xrot, g_mean, g_lrfs,
