@@ -38,30 +38,70 @@ def init_from_env(backend=None):
 
 class FlatGradBucket:
     """All parameter gradients as views into one contiguous FP32 buffer, so the step's
-    only collective is a single all-reduce of ~3.7 MB (QecNet, 40 classes)."""
+    only exchange is an all-reduce of ~3.7 MB (QecNet, 40 classes).
 
-    def __init__(self, params):
-        self.params = [p for p in params if p.requires_grad]
-        if not self.params:
+    `early`: parameters whose gradients are complete well before the end of the backward pass (pool2 of
+    QEC-Net: 90 % of the bytes, done when 40 % of the backward is still to run).  They are laid out first
+    in the buffer and their slice is all-reduced ASYNCHRONOUSLY as soon as the last of them has been
+    accumulated (post-accumulate-grad hooks), so the transfer overlaps the rest of the backward instead
+    of being exposed at the end of the step; all_reduce_mean() then reduces the small remainder and
+    joins.  Every rank launches the same two collectives in the same order.  Protocol per step:
+    zero() -> forward -> backward -> all_reduce_mean(); a backward that is NOT followed by
+    all_reduce_mean() must run with `overlap = False`."""
+
+    def __init__(self, params, early=None):
+        params = [p for p in params if p.requires_grad]
+        if not params:
             raise ValueError("no trainable parameters")
+        early_ids = {id(p) for p in (early or [])}
+        self.early = [p for p in params if id(p) in early_ids]
+        self.params = self.early + [p for p in params if id(p) not in early_ids]
         dev = self.params[0].device
         n = sum(p.numel() for p in self.params)
+        self.n_early = sum(p.numel() for p in self.early)
         self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
+        self._seen = 0
+        self._work = None
+        self._group = None
+        self.overlap = True  # set to False for a backward pass that must not touch the network (no all_reduce_mean after it)
+        for p in self.early:
+            p.register_post_accumulate_grad_hook(self._on_early_grad)
+
+    def _distributed(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self._group) > 1
+
+    def _on_early_grad(self, _param):
+        self._seen += 1
+        if self._seen == len(self.early):
+            self._seen = 0
+            if self.overlap and self._distributed() and self._work is None:
+                self._work = dist.all_reduce(self.flat[:self.n_early], op=dist.ReduceOp.SUM, group=self._group,
+                                             async_op=True)
 
     def zero(self):
+        if self._work is not None:  # a reduction nobody joined: finish it before the buffer is reused
+            self._work.wait()
+            self._work = None
         self.flat.zero_()
+        self._seen = 0
 
     def all_reduce_mean(self, group=None):
         """sum over ranks / world size: the loss is a mean over the GLOBAL batch"""
-        if dist.is_available() and dist.is_initialized():
+        self._group = group
+        if self._distributed():
             world = dist.get_world_size(group)
-            if world > 1:
+            if self._work is not None:  # the early slice is already in flight
+                if self.n_early < self.flat.numel():
+                    dist.all_reduce(self.flat[self.n_early:], op=dist.ReduceOp.SUM, group=group)
+                self._work.wait()
+                self._work = None
+            else:
                 dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-                self.flat.div_(world)
+            self.flat.div_(world)
 
     def nbytes(self):
         return self.flat.numel() * 4

@@ -22,7 +22,7 @@ def _worker(rank, world, port, out):
     torch.manual_seed(7)
     net = qb.QecNet(2048, 16, 10, 3).to(dev)
     ddp.broadcast_parameters(net, 0)
-    bucket = ddp.FlatGradBucket(net.parameters())
+    bucket = ddp.FlatGradBucket(net.parameters(), early=list(net.pool2.parameters()))  # overlapped slice
     B = 4
     points, lrfs, act, labels = [t.to(dev) for t in synthetic_batch(B * world, ncls=10, seed=11)]
     lo, hi = ddp.shard_batch(B * world, rank, world)
@@ -31,7 +31,8 @@ def _worker(rank, world, port, out):
     net.spread_loss(a, labels[lo:hi]).backward()
     bucket.all_reduce_mean()
     got = bucket.flat.clone()
-    # the same global batch on one device
+    # the same global batch on one device (a local backward: no collective may be launched by the hooks)
+    bucket.overlap = False
     bucket.zero()
     _, a = net(points, lrfs, act, None)
     net.spread_loss(a, labels).backward()

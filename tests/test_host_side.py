@@ -138,6 +138,18 @@ def _ddp_worker(rank, world, port, out):
     bucket.all_reduce_mean()
     expect = sum(range(1, world + 1)) / world
     ok = all(torch.allclose(p.grad, torch.full_like(p, expect * (i + 1))) for i, p in enumerate(net.parameters()))
+    # early slice: reduced asynchronously from the post-accumulate hooks of a real backward, joined afterwards
+    net2 = qb.QecNet(2048, 4, 5, 3)
+    ddp.broadcast_parameters(net2, 0)
+    b2 = ddp.FlatGradBucket(net2.parameters(), early=list(net2.pool2.parameters()))
+    assert b2.n_early == sum(p.numel() for p in net2.pool2.parameters())
+    b2.zero()
+    loss = sum((p * float(rank + 1) * (i + 1)).sum() for i, p in enumerate(net2.parameters()))
+    loss.backward()
+    launched_early = b2._work is not None
+    b2.all_reduce_mean()
+    ok = ok and launched_early and all(
+        torch.allclose(p.grad, torch.full_like(p, expect * (i + 1))) for i, p in enumerate(net2.parameters()))
     first = next(net.parameters()).detach().clone()
     gathered = [torch.zeros_like(first) for _ in range(world)]
     dist.all_gather(gathered, first)
