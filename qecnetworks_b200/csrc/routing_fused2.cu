@@ -756,18 +756,19 @@ __device__ __forceinline__ void bwd2_acc_sweep(int np, const Bwd2Geom& B, const 
     for (int i = 0; i < 14; ++i) a2[i] = bc(0.f);
     float sabs = 0.f;
     OffWalk wp = w0;
-    auto lda = [&](int m, f2& a) {  // activations run one slot ahead (L2-resident: shared by all O)
+    auto lda = [&](int m, f2& a) {  // activations run ahead of their use (L2-resident: shared by all O)
         const int ps = threadIdx.x + m * kPT;
         if (FULL || ps < np) a = ldg_f2(B.act + (size_t)B.offA + 2 * ps);
     };
-    f2 an[2];
+    f2 an[3];  // two slots ahead: one was not enough under the prefetch traffic of the last sweep
     lda(0, an[0]);
+    lda(1, an[1]);
 #pragma unroll
     for (int m = 0; m < kPairs; ++m) {
-        if (m + 1 < kPairs) lda(m + 1, an[(m + 1) & 1]);
+        if (m + 2 < kPairs) lda(m + 2, an[(m + 2) % 3]);
         const int ps = threadIdx.x + m * kPT;
         if (FULL || ps < np) {
-            const f2 a = an[m & 1];
+            const f2 a = an[m % 3];
             const Quat2 v = lds_pair(sA, sB, ps);
             const f2 om0 = (T >= 2) ? lds_f2(som0 + ps) : bc(1.f);
             const f2 om1 = (T >= 3) ? lds_f2(som1 + ps) : bc(1.f);
@@ -924,9 +925,10 @@ __global__ void __launch_bounds__(kPT, 2)
         // poses_all (L2) and the adjoint vectors u^t / 1/S^t from a 32-float shared array, so that each
         // sweep only keeps what it uses live (the 28 registers of the full state made the sweeps spill).
         const float s = __ldg(stats + 2 * c), n = __ldg(stats + 2 * c + 1);
+        const float g_agr_c = __ldg(g_agr + c);  // unconditional: one L2 round trip for all three, not two in series
         const bool has = n > 0.f;
         const float sg = sigmoidf(fmaf(alpha, s, beta - 1.f));
-        const float gz = has ? __ldg(g_agr + c) * sg * (1.f - sg) : 0.f;
+        const float gz = has ? g_agr_c * sg * (1.f - sg) : 0.f;
         ga_tot += gz * s;
         gb_tot += gz;
         const float gsn = has ? gz * alpha / n : 0.f;
@@ -957,17 +959,23 @@ __global__ void __launch_bounds__(kPT, 2)
         for (int k = 1; k <= nsweeps; ++k) {
             const int t = T - k;  // level being completed
             QEC_EVT(7 * (k - 1) + 1);
+            // the solver's own operands are requested before the reduction, not on the serial path behind it
+            // (an L2 round trip per chain: backward 1.32 -> 1.28 ms at config 2)
+            Quat p = qmake(0.f, 0.f, 0.f, 0.f), gp_top = qmake(0.f, 0.f, 0.f, 0.f);
+            if (red.solver()) {
+                p = ldq_nc(poses_all + ((size_t)t * Nc + c) * 4);
+                if (t == T - 1) gp_top = ldq_nc(g_pose + (size_t)c * 4);
+            }
 #ifdef QEC_PROF
             red.reduce(acc, 7 * (k - 1) + 2, prof_n);
 #else
             red.reduce(acc);      // sums of the level accumulated by the previous sweep
 #endif
             if (red.solver()) {
-                const Quat p = ldq_nc(poses_all + ((size_t)t * Nc + c) * 4);
                 const float rs = 1.f / fmaxf(acc[14], 1e-12f);
                 const Sym4 m = acc_to_sym(acc + 4, rs);
                 Quat gp = qmake(acc[0], acc[1], acc[2], acc[3]);
-                if (t == T - 1) gp = qadd(gp, ldq_nc(g_pose + (size_t)c * 4));
+                if (t == T - 1) gp = qadd(gp, gp_top);
                 const float lam = qdot(p, sym_mul(m, p));
                 Quat u = top_eigvec_adjoint(m, p, lam, gp);
                 if (!(qdot(p, p) > 0.5f)) u = qmake(0.f, 0.f, 0.f, 0.f);  // invalid / sign-zeroed pose

@@ -27,3 +27,18 @@ for _ in range(10):
 torch.cuda.synchronize()
 for (name, dims), ts in _lib.stop_kernel_timing().items():
     print("%s %.3f ms (min %.3f)" % (name, sum(ts) / len(ts), min(ts)))
+
+# the same backward through the raw entry points, plain and pre-split (what the one-node GEMM + routing path calls)
+with torch.no_grad():
+    pose, agr, poses_all, stats = QF.routing_fused_forward_raw(t_oqi, lrfs, act, alpha, beta, T)
+    gp, ga = torch.ones_like(pose), torch.ones_like(agr)
+    for split in (False, True):
+        for _ in range(3):
+            QF.routing_fused_backward_raw(t_oqi, lrfs, act, alpha, beta, poses_all, stats, gp, ga, T, True, True, split=split)
+        torch.cuda.synchronize()
+        _lib.start_kernel_timing()
+        for _ in range(10):
+            QF.routing_fused_backward_raw(t_oqi, lrfs, act, alpha, beta, poses_all, stats, gp, ga, T, True, True, split=split)
+        torch.cuda.synchronize()
+        for (name, dims), ts in _lib.stop_kernel_timing().items():
+            print("raw %s %.3f ms (min %.3f)" % (name, sum(ts) / len(ts), min(ts)))
