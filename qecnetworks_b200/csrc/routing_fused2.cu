@@ -685,24 +685,53 @@ __device__ __forceinline__ void prefetch_walk(const Bwd2Geom& B, size_t offT_nex
 // ---- top level, pass 1: dL/dvote of the level whose votes are not detached -> dL/dt_raw, dL/dlrf.
 // No accumulators are live here; the accumulation of level T-2 is a separate pass (bwd2_acc_sweep),
 // which keeps both under the 128-register budget of two CTAs per SM.
+// Without PREFETCH (the chained backward) the pair's transforms and activations are STAGED: while slot m is
+// computed, slot m + 1's 40 bytes per thread travel global -> shared by cp.async into the reducer's scratch,
+// which is idle between two reductions (each thread reads back only what it copied itself: no barrier).
+// One pair in flight leaves ~100 instructions between a direct load and its first use, and no registers
+// for a second pair.
 template <int T, bool FULL, bool PREFETCH>
 __device__ __forceinline__ void bwd2_grad_pass(int np, const Bwd2Geom& B, const Bwd2Caps& C, OffWalk w0, float4* sA,
-                                               float4* sB, size_t offT_next) {
+                                               float4* sB, size_t offT_next, float* stage_f) {
     constexpr int TT = T - 1;
+    constexpr bool STAGE = !PREFETCH;  // PREFETCH owns the cp.async group count of the next capsule's sweep 0
     float2* som0 = reinterpret_cast<float2*>(sB + kNpMax);
     float2* som1 = som0 + kNpMax;
-    OffWalk w = w0, wp = w0;
+    float2* stage = reinterpret_cast<float2*>(stage_f) + threadIdx.x;  // [5][kPT] float2: t rows w,x,y,z and a
+    OffWalk w = w0, wp = w0, ws = w0;
+    auto stage_slot = [&](int m) {  // ws walks one slot ahead of w
+        const int ps = threadIdx.x + m * kPT;
+        if (FULL || ps < np) {
+            const float* tp = B.t_oqi + (B.offT + (size_t)ws.off);
+            cp_async8(stage, tp);
+            cp_async8(stage + kPT, tp + B.I);
+            cp_async8(stage + 2 * kPT, tp + 2 * B.I);
+            cp_async8(stage + 3 * kPT, tp + 3 * B.I);
+            cp_async8(stage + 4 * kPT, B.act + (size_t)B.offA + 2 * ps);
+        }
+        cp_async_commit();
+        ws.next(B);
+    };
+    if (STAGE) stage_slot(0);
 #pragma unroll 1  // one pair in flight: ~70 live registers per pair leave no room to overlap two
     for (int m = 0; m < kPairs; ++m) {
         const int ps = threadIdx.x + m * kPT;
+        if (STAGE) cp_async_wait<0>();
         if (FULL || ps < np) {
-            // issued first: the level walk below hides their latency
-            const float* tp = B.t_oqi + (B.offT + (size_t)w.off);
             Quat2 traw;
-            traw.w = ldg_f2(tp); traw.x = ldg_f2(tp + B.I); traw.y = ldg_f2(tp + 2 * B.I); traw.z = ldg_f2(tp + 3 * B.I);
+            f2 a;
             const float* lp = B.lrfs + ((size_t)B.offA + 2 * ps) * 4;
             const Quat2 lrf = pk(ldq_nc(lp), ldq_nc(lp + 4));
-            const f2 a = ldg_f2(B.act + (size_t)B.offA + 2 * ps);
+            if (STAGE) {
+                traw.w = lds_f2(stage); traw.x = lds_f2(stage + kPT); traw.y = lds_f2(stage + 2 * kPT); traw.z = lds_f2(stage + 3 * kPT);
+                a = lds_f2(stage + 4 * kPT);
+            } else {
+                // issued first: the level walk below hides part of their latency
+                const float* tp = B.t_oqi + (B.offT + (size_t)w.off);
+                traw.w = ldg_f2(tp); traw.x = ldg_f2(tp + B.I); traw.y = ldg_f2(tp + 2 * B.I); traw.z = ldg_f2(tp + 3 * B.I);
+                a = ldg_f2(B.act + (size_t)B.offA + 2 * ps);
+            }
+            if (STAGE && m + 1 < kPairs) stage_slot(m + 1);  // after this slot's operands have been read back
             const Quat2 v = lds_pair(sA, sB, ps);
             f2 b = a;
             if (T >= 2) b = mul2(b, mul2(a, lds_f2(som0 + ps)));
@@ -993,8 +1022,8 @@ __global__ void __launch_bounds__(kPT, 2)
 #define QEC_BWD_GRAD(T_)                                                                       \
     {                                                                                          \
         const Bwd2Caps C = caps(T_ - 1, T_ - 1);                                               \
-        if (pf_grad) bwd2_grad_pass<T_, FULL, true>(np, B, C, w0, sA, sB, offT_next);          \
-        else bwd2_grad_pass<T_, FULL, false>(np, B, C, w0, sA, sB, offT_next);                 \
+        if (pf_grad) bwd2_grad_pass<T_, FULL, true>(np, B, C, w0, sA, sB, offT_next, red.scr);          \
+        else bwd2_grad_pass<T_, FULL, false>(np, B, C, w0, sA, sB, offT_next, red.scr);                 \
         QEC_EVT(7);                                                                            \
     }
 #define QEC_BWD_ACC(TT_, T_)                                                                   \
