@@ -305,7 +305,10 @@ def run_b200(a):
     ddp.broadcast_parameters(net, 0)
     # pool2's gradients (90 % of the bytes) are all-reduced while the pool1 backward still runs
     bucket = ddp.FlatGradBucket(net.parameters(), early=list(net.pool2.parameters()))
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=True, fused=True)  # train_cls.py:44-51 (one fused kernel)
+    # train_cls.py:44-51 (Adam, default betas/eps): one launch over the flat buffers, which also applies the
+    # 1/world of the all-reduce and re-zeroes the gradient buffer (tests/test_gpu_adam.py: == torch.optim.Adam)
+    opt = ddp.FlatAdam(bucket, lr=1e-3)
+    bucket.zero()
 
     NB = 4  # distinct batches rotated through the timed region
     host = [synthetic_batch(a.batch, ncls=a.classes, seed=1234 + 1000 * rank + i, pin=True) for i in range(NB)]
@@ -313,12 +316,10 @@ def run_b200(a):
     h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
 
     def train_step(points, lrfs, act, labels):
-        bucket.zero()
         _, agr = net(points, lrfs, act, None)
         loss = net.spread_loss(agr, labels)
         loss.backward()
-        bucket.all_reduce_mean()
-        opt.step()
+        opt.step(grad_scale=bucket.all_reduce_mean(average=False))
         return loss
 
     # optional CUDA graph of the whole step (static input buffers)

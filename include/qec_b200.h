@@ -190,6 +190,16 @@ int qec_fold_chunks(const float* a, const float* b, const long long* perm, float
 int qec_spread_loss(const float* x, const long long* labels, float margin, float* loss, float* g_x, float* scratch,
                     int* err, int B, int C, void* stream);
 
+/* One Adam step (reference train_cls.py:44-51: torch.optim.Adam, default betas / eps) on FLAT FP32 buffers of n
+ * elements, 16-byte aligned -- parameters, gradient, first and second moment (qecnetworks_b200/ddp.py lays the
+ * network's tensors out as views of such buffers).  The gradient is read as grads * grad_scale (1/world after a
+ * summing all-reduce) and overwritten with zeros when zero_grad != 0, so the step needs neither a scaling pass
+ * nor a memset.  Bias corrections 1 - beta^t are evaluated in double like torch's; weight_decay is torch's L2
+ * form (added to the gradient).  state: two device ints, zeroed by the caller before the first step ({steps
+ * taken, scratch}); the kernel advances the count itself, so the call is CUDA-graph capturable. */
+int qec_adam_flat(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, double beta1,
+                  double beta2, float eps, float weight_decay, float grad_scale, int zero_grad, int* state, void* stream);
+
 /* FP32 FMA roof: blocks*256 threads x iters x 16 dependent-chain FMAs
  * (2*16*iters*256*blocks FLOP); timed by the caller with CUDA events.  No reference
  * counterpart: it measures the denominator of the FP32 roofline on the box. */

@@ -13,6 +13,7 @@ _P = ctypes.c_void_p
 _I = ctypes.c_int
 _LL = ctypes.c_longlong
 _F = ctypes.c_float
+_D = ctypes.c_double
 
 # name -> (argtypes, kernels launched per call)
 SIGNATURES = {
@@ -40,6 +41,7 @@ SIGNATURES = {
     "qec_split_operand": ([_P, _P, _F, _P, _P, _P, _LL, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], 1),
     "qec_fold_chunks": ([_P, _P, _P, _P, _P, _I, _LL, _I, _I, _I, _P], 1),
     "qec_spread_loss": ([_P, _P, _F, _P, _P, _P, _P, _I, _I, _P], 2),
+    "qec_adam_flat": ([_P, _P, _P, _P, _LL, _F, _D, _D, _F, _F, _F, _I, _P, _P], 1),
     "qec_ffma_peak": ([_P, _I, _I, _P], 1),
     "qec_pipe_probe": ([_P, _I, _I, _I, _P], 1),
 }

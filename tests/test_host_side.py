@@ -150,6 +150,14 @@ def _ddp_worker(rank, world, port, out):
     b2.all_reduce_mean()
     ok = ok and launched_early and all(
         torch.allclose(p.grad, torch.full_like(p, expect * (i + 1))) for i, p in enumerate(net2.parameters()))
+    # average=False: the buffer keeps the SUM and the caller is told what is owed (FlatAdam's grad_scale)
+    b2.zero()
+    b2.overlap = False
+    for i, p in enumerate(net2.parameters()):
+        p.grad.add_(float(rank + 1) * (i + 1))
+    owed = b2.all_reduce_mean(average=False)
+    ok = ok and owed == 1.0 / world and all(
+        torch.allclose(p.grad, torch.full_like(p, expect * world * (i + 1))) for i, p in enumerate(net2.parameters()))
     first = next(net.parameters()).detach().clone()
     gathered = [torch.zeros_like(first) for _ in range(world)]
     dist.all_gather(gathered, first)
@@ -165,3 +173,29 @@ def test_flat_bucket_allreduce_gloo_world2():
     port = 29611 + os.getpid() % 200
     mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+def test_flat_adam_host_layout_and_no_cpu_fallback():
+    """FlatAdam re-points the parameters at one flat buffer in the bucket's order (values unchanged, early
+    slice first) and refuses to step on CPU tensors: the optimizer kernel is CUDA-only like the rest."""
+    import qecnetworks_b200 as qb
+    from qecnetworks_b200 import ddp, _lib
+
+    torch.manual_seed(3)
+    net = qb.QecNet(2048, 4, 5, 3)
+    before = {k: v.detach().clone() for k, v in net.named_parameters()}
+    bucket = ddp.FlatGradBucket(net.parameters(), early=list(net.pool2.parameters()))
+    opt = ddp.FlatAdam(bucket, lr=1e-3)
+    assert bucket.all_reduce_mean(average=False) == 1.0  # single process: nothing owed
+    off = 0
+    for p in bucket.params:
+        n = p.numel()
+        assert p.data_ptr() == opt.flat.data_ptr() + 4 * off  # a view of the flat parameter buffer ...
+        assert p.grad.data_ptr() == bucket.flat.data_ptr() + 4 * off  # ... at the offset of its gradient
+        off += n
+    assert off == opt.flat.numel() == bucket.flat.numel()
+    for k, v in net.named_parameters():
+        assert torch.equal(v.detach(), before[k])
+    assert bucket.params[0] is next(net.pool2.parameters())
+    with pytest.raises(_lib.QecLibraryError):
+        opt.step()
