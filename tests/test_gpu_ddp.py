@@ -38,7 +38,28 @@ def _worker(rank, world, port, out):
     net.spread_loss(a, labels).backward()
     ref = bucket.flat.clone()
     err = float((got - ref).abs().max() / ref.abs().max())
-    out[rank] = err
+    # the training step of bench.py: the SUM stays in the bucket, FlatAdam applies the 1/world it is owed and
+    # leaves the bucket zeroed; every rank must end with the parameters torch.optim.Adam gives for the same
+    # averaged gradient
+    import copy
+
+    ref_net = copy.deepcopy(net)  # parameters as they are now; its own gradient tensors
+    topt = torch.optim.Adam(ref_net.parameters(), lr=1e-3)
+    opt = ddp.FlatAdam(bucket, lr=1e-3)
+    bucket.overlap = True
+    bucket.zero()
+    _, a = net(points[lo:hi], lrfs[lo:hi], act[lo:hi], None)
+    net.spread_loss(a, labels[lo:hi]).backward()
+    owed = bucket.all_reduce_mean(average=False)
+    assert owed == 1.0 / world
+    for p, q in zip(net.parameters(), ref_net.parameters()):
+        q.grad = p.grad.detach().clone() * owed
+    gerr = float((bucket.flat * owed - ref).abs().max() / ref.abs().max())  # still the global-batch gradient
+    topt.step()
+    opt.step(grad_scale=owed)
+    perr = max(float((p.detach() - q.detach()).abs().max()) for p, q in zip(net.parameters(), ref_net.parameters()))
+    zeroed = float(bucket.flat.abs().max()) == 0.0
+    out[rank] = max(err, gerr) if (perr < 2e-6 and zeroed) else 1.0 + perr
     dist.barrier()
     dist.destroy_process_group()
 
