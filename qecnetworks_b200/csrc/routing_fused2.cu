@@ -32,13 +32,27 @@
 // geometries use the scalar kernels of routing_fused.cu.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "f32x2.cuh"
 #include "routing_core.cuh"
 #include "routing_fused_shared.cuh"
 
 namespace cg = cooperative_groups;
 
+// The file is compiled twice: as itself (256 threads per CTA, two CTAs per SM, clusters of up to 8) and through
+// routing_fused2_wide.cu (QEC_PT = 512: ONE CTA of 16 warps per SM holding 8 192 votes, clusters of up to 4).
+// Each build lives in its own nested namespace; the C entry points belong to the 256-thread build and hand
+// the geometries that would need an 8-CTA cluster to the wide one (see qec_fused2_wide_* at the end).
+#ifndef QEC_PT
+#define QEC_PT 256
+#endif
+#ifndef QEC_VARIANT_NS
+#define QEC_VARIANT_NS pt256
+#endif
+
 namespace qec {
+namespace QEC_VARIANT_NS {
 
 // Optional timeline instrumentation (build with QEC_NVCC_EXTRA=-DQEC_PROF; scripts/timeline_fused.py):
 // thread 0 of a few CTAs stamps clock64() at the phase boundaries of its first capsules.
@@ -58,7 +72,8 @@ __device__ long long g_prof[8 * 64 * 32];
     } while (0)
 #endif
 
-constexpr int kPT = 256;         // threads per CTA
+constexpr int kPT = QEC_PT;      // threads per CTA
+constexpr int kCtasPerSM = (kPT <= 256) ? 2 : 1;
 constexpr int kPairs = 8;        // resident vote pairs per thread
 constexpr int kNpMax = kPT * kPairs;  // 2048 pairs = 4096 votes per CTA
 
@@ -161,10 +176,12 @@ struct PushReducer {
         const int v = tid >> 4, part = tid & 15;
         float s = 0.f;
         if (v < N) {
-            const float4* row = reinterpret_cast<const float4*>(scr + v * NT + part * 16);
+            constexpr int kPer = NT / 16;  // entries per lane: 16 (256 threads) or 32 (512 threads)
+            const float4* row = reinterpret_cast<const float4*>(scr + v * NT + part * kPer);
+            const int rot = (kPer == 16) ? (part >> 1) : part;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {  // rotated start: conflict-free LDS.128
-                const float4 q = row[((part >> 1) + k) & 3];
+            for (int k = 0; k < kPer / 4; ++k) {  // rotated start: conflict-free LDS.128
+                const float4 q = row[(rot + k) & (kPer / 4 - 1)];
                 s += (q.x + q.y) + (q.z + q.w);
             }
         }
@@ -310,7 +327,7 @@ __device__ __forceinline__ void wait_slot() {  // slot M's group is complete (gr
 // FULL: every thread owns exactly kPairs resident pairs (J == CL * 4096, e.g. pool2 of QEC-Net):
 // no per-slot guards, so the unrolled sweeps are straight-line code the scheduler can interleave.
 template <int CL, bool FULL>
-__global__ void __launch_bounds__(kPT, 2)
+__global__ void __launch_bounds__(kPT, kCtasPerSM)
     routing_fused2_fwd_kernel(const float* __restrict__ t_oqi, const float* __restrict__ lrfs,
                               const float* __restrict__ act, const float* __restrict__ alpha_p,
                               const float* __restrict__ beta_p, float* __restrict__ pose,
@@ -886,7 +903,7 @@ __device__ __forceinline__ void bwd2_sweep0(int np, const Bwd2Geom& B, const Bwd
 }
 
 template <int CL, bool FULL>
-__global__ void __launch_bounds__(kPT, 2)
+__global__ void __launch_bounds__(kPT, kCtasPerSM)
     routing_fused2_bwd_kernel(const float* __restrict__ t_oqi, const float* __restrict__ lrfs,
                               const float* __restrict__ act, const float* __restrict__ alpha_p,
                               const float* __restrict__ beta_p, const float* __restrict__ poses_all,
@@ -1084,9 +1101,79 @@ static int launch_fused2_bwd(const float* t_oqi, const float* lrfs, const float*
     return e == cudaSuccess ? launch_status() : (int)e;
 }
 
+}  // namespace QEC_VARIANT_NS
 }  // namespace qec
 
 using namespace qec;
+using namespace qec::QEC_VARIANT_NS;
+
+#ifdef QEC_WIDE
+// ------------------------------------------------------------------------------------
+// The 512-thread build (routing_fused2_wide.cu): the same kernels with ONE CTA of 16 warps per SM that
+// holds 8 192 votes, so a capsule of 32 768 votes needs a cluster of 4 instead of 8.  Clusters of 4 tile the
+// GPCs without a remainder (37 capsules in flight on 148 SMs instead of 33 on 132), all sixteen warps of an
+// SM sweep the same capsule (the fma pipe is saturated without a second, independent CTA) and the
+// reduce -> solve -> publish chain runs unloaded -- but nothing runs in its shadow.  Net effect measured at
+// use_wide() below.  Internal entry points, called by the public ones.
+// ------------------------------------------------------------------------------------
+static int pick_cluster_wide(long long J) {
+    for (int cl = 1; cl <= 4; cl *= 2)
+        if ((J + cl - 1) / cl <= 2ll * kNpMax) return cl;
+    return 0;
+}
+#define QEC_DISPATCH_CL_WIDE(FN, ...)          \
+    switch (CL) {                              \
+        case 1: return FN<1>(__VA_ARGS__);     \
+        case 2: return FN<2>(__VA_ARGS__);     \
+        default: return FN<4>(__VA_ARGS__);    \
+    }
+
+extern "C" int qec_fused2_wide_fwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
+                                   const float* beta, float* pose, float* agreement, float* poses_all, float* stats,
+                                   int BP, int K, int I, int O, int T, void* stream) {
+    const int CL = pick_cluster_wide((long long)K * I);
+    QEC_CHECK_ARG(CL > 0, 11);
+    const long long Nc = (long long)BP * O;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    QEC_DISPATCH_CL_WIDE(launch_fused2_fwd, t_oqi, lrfs, act, alpha, beta, pose, agreement, poses_all, stats, Nc, K, I,
+                         O, T, st)
+}
+
+extern "C" int qec_fused2_wide_bwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
+                                   const float* beta, const float* poses_all, const float* stats, const float* g_pose,
+                                   const float* g_agreement, float* g_toqi, unsigned short* g_lo, float* g_lrfs,
+                                   float* g_act, float* g_alpha_beta, int BP, int K, int I, int O, int T, void* stream) {
+    const int CL = pick_cluster_wide((long long)K * I);
+    QEC_CHECK_ARG(CL > 0, 15);
+    const long long Nc = (long long)BP * O;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    QEC_DISPATCH_CL_WIDE(launch_fused2_bwd, t_oqi, lrfs, act, alpha, beta, poses_all, stats, g_pose, g_agreement, g_toqi,
+                         g_lo, g_lrfs, g_act, g_alpha_beta, Nc, K, I, O, T, st)
+}
+
+#else  // ---------------- the 256-thread build owns the public entry points ----------------
+
+extern "C" int qec_fused2_wide_fwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
+                                   const float* beta, float* pose, float* agreement, float* poses_all, float* stats,
+                                   int BP, int K, int I, int O, int T, void* stream);
+extern "C" int qec_fused2_wide_bwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
+                                   const float* beta, const float* poses_all, const float* stats, const float* g_pose,
+                                   const float* g_agreement, float* g_toqi, unsigned short* g_lo, float* g_lrfs,
+                                   float* g_act, float* g_alpha_beta, int BP, int K, int I, int O, int T, void* stream);
+
+// Geometries that need an 8-CTA cluster of the 256-thread build can go to the 512-thread build (clusters of 4).
+// Measured at BASELINE config 2 (scripts/time_pool2.py): forward 0.514 -> 0.526 ms (its chains have nothing to
+// hide behind when the CTA is alone on its SM: the gain of 37 instead of 33 capsules in flight is spent on
+// them), backward 1.134 -> 1.124 ms plain, 1.188 -> 1.176 ms pre-split.  Default: backward only.
+// QEC_FUSED_WIDE = 0 (never) | 1 (both) | f (forward only) | b (backward only) for A/B timing.
+static bool use_wide(long long J, bool backward) {
+    static const char mode = [] {
+        const char* e = getenv("QEC_FUSED_WIDE");
+        return (e != nullptr && e[0] != 0) ? e[0] : 'b';
+    }();
+    const bool on = mode == '1' || (backward ? mode == 'b' : mode == 'f');
+    return on && pick_cluster((int)J) == 8;
+}
 
 // 1 if the packed-pair kernels serve this geometry (callers normally just call qec_routing_fused_*,
 // which dispatch here when possible)
@@ -1109,6 +1196,8 @@ extern "C" int qec_routing_fused_fwd(const float* t_oqi, const float* lrfs, cons
     QEC_CHECK_ARG(act && alpha && beta, 3);
     QEC_CHECK_ARG(pose && agreement && poses_all && stats, 6);
     QEC_CHECK_ARG(BP > 0, 10);
+    if (use_wide((long long)K * I, false))
+        return qec_fused2_wide_fwd(t_oqi, lrfs, act, alpha, beta, pose, agreement, poses_all, stats, BP, K, I, O, T, stream);
     const int CL = pick_cluster(K * I);
     const long long Nc = (long long)BP * O;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1118,7 +1207,7 @@ extern "C" int qec_routing_fused_fwd(const float* t_oqi, const float* lrfs, cons
 
 #ifdef QEC_PROF
 extern "C" int qec_prof_read(long long* dst_host) {
-    return (int)cudaMemcpyFromSymbol(dst_host, qec::g_prof, sizeof(long long) * 8 * 64 * 32);
+    return (int)cudaMemcpyFromSymbol(dst_host, g_prof, sizeof(long long) * 8 * 64 * 32);
 }
 #endif
 
@@ -1132,6 +1221,9 @@ static int fused2_bwd_entry(const float* t_oqi, const float* lrfs, const float* 
     QEC_CHECK_ARG(g_pose && g_agreement, 8);
     QEC_CHECK_ARG(g_toqi && g_alpha_beta, 10);
     QEC_CHECK_ARG(BP > 0, 14);
+    if (use_wide((long long)K * I, true))
+        return qec_fused2_wide_bwd(t_oqi, lrfs, act, alpha, beta, poses_all, stats, g_pose, g_agreement, g_toqi, g_lo,
+                                   g_lrfs, g_act, g_alpha_beta, BP, K, I, O, T, stream);
     const int CL = pick_cluster(K * I);
     const long long Nc = (long long)BP * O;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1165,3 +1257,4 @@ extern "C" int qec_routing_fused_bwd_split(const float* t_oqi, const float* lrfs
     return fused2_bwd_entry(t_oqi, lrfs, act, alpha, beta, poses_all, stats, g_pose, g_agreement, g_toqi_hi, g_toqi_lo,
                             g_lrfs, g_act, g_alpha_beta, BP, K, I, O, T, stream);
 }
+#endif  // QEC_WIDE

@@ -8,7 +8,7 @@ from qecnetworks_b200 import functional as QF
 dev = torch.device("cuda:0")
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 shapes = [(2, 1, 64, 32, 5, 3), (1, 2, 100, 37, 3, 3), (1, 1, 256, 24, 4, 3), (1, 1, 250, 50, 3, 2),
-          (2, 1, 256, 128, 40, 3), (1, 1, 256, 128, 6, 1)]
+          (2, 1, 256, 128, 40, 3), (1, 1, 256, 128, 6, 1), (1, 1, 250, 100, 3, 3)]
 bad = 0
 for (B, P, K, I, O, T) in shapes:
     g = torch.Generator().manual_seed(K + I)

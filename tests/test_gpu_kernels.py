@@ -306,8 +306,10 @@ def _oqi_perm(I, O):
         (1, 2, 100, 37, 3, 3),    # J = 3700, ragged channels
         (1, 1, 256, 24, 4, 3),    # J = 6144, cluster of 2
         (1, 1, 250, 50, 3, 2),    # J = 12500, cluster of 4, ragged split, T = 2
-        (1, 1, 256, 128, 6, 3),   # J = 32768, cluster of 8 (pool2 of BASELINE config 2)
+        (1, 1, 256, 128, 6, 3),   # J = 32768 (pool2 of BASELINE config 2): 4 CTAs x 512 threads, every CTA full
         (1, 1, 256, 128, 2, 1),   # T = 1
+        (1, 2, 250, 100, 3, 3),   # J = 25000: the 512-thread build with a ragged split
+        (2, 1, 129, 128, 2, 2),   # J = 16512: just above two full 8 192-vote CTAs, last CTA nearly empty
     ],
 )
 def test_routing_fused(B, P, K, I, O, T):
@@ -377,8 +379,9 @@ def test_routing_fused(B, P, K, I, O, T):
 @pytest.mark.parametrize(
     "B,P,K,I,O,T",
     [
-        (2, 1, 256, 128, 3, 3),   # cluster of 8, every CTA full (the guard-free instantiation)
+        (2, 1, 256, 128, 3, 3),   # J = 32768, every CTA full (the guard-free instantiation of the 512-thread build)
         (1, 1, 256, 128, 3, 2),   # ... T = 2
+        (1, 1, 250, 90, 2, 3),    # J = 22500: 512-thread build, ragged
         (1, 1, 128, 128, 2, 3),   # cluster of 4, full
         (1, 1, 64, 128, 2, 3),    # cluster of 2, full
         (1, 2, 32, 128, 2, 3),    # one CTA per capsule, full
