@@ -190,6 +190,13 @@ int qec_fold_chunks(const float* a, const float* b, const long long* perm, float
 int qec_spread_loss(const float* x, const long long* labels, float margin, float* loss, float* g_x, float* scratch,
                     int* err, int B, int C, void* stream);
 
+/* Which build of the packed cluster-resident routing kernels serves capsules of more than 16 384 votes:
+ * 0 = 256 threads per CTA, two CTAs per SM, clusters of 8 (default); 1 = 512 threads, one CTA per SM, clusters
+ * of 4, forward and backward; 2 = forward only; 3 = backward only.  Same results either way (tests run both).
+ * Initial value from the environment (QEC_FUSED_WIDE = 0 | 1 | f | b).  Returns the previous mode; an
+ * out-of-range argument only queries.  No reference counterpart. */
+int qec_routing_fused_set_wide(int mode);
+
 /* One Adam step (reference train_cls.py:44-51: torch.optim.Adam, default betas / eps) on FLAT FP32 buffers of n
  * elements, 16-byte aligned -- parameters, gradient, first and second moment (qecnetworks_b200/ddp.py lays the
  * network's tensors out as views of such buffers).  The gradient is read as grads * grad_scale (1/world after a

@@ -1161,18 +1161,28 @@ extern "C" int qec_fused2_wide_bwd(const float* t_oqi, const float* lrfs, const 
                                    const float* g_agreement, float* g_toqi, unsigned short* g_lo, float* g_lrfs,
                                    float* g_act, float* g_alpha_beta, int BP, int K, int I, int O, int T, void* stream);
 
-// Geometries that need an 8-CTA cluster of the 256-thread build can go to the 512-thread build (clusters of 4).
-// Measured at BASELINE config 2 (scripts/time_pool2.py): forward 0.514 -> 0.526 ms (its chains have nothing to
-// hide behind when the CTA is alone on its SM: the gain of 37 instead of 33 capsules in flight is spent on
-// them), backward 1.134 -> 1.124 ms plain, 1.188 -> 1.176 ms pre-split.  Default: backward only.
-// QEC_FUSED_WIDE = 0 (never) | 1 (both) | f (forward only) | b (backward only) for A/B timing.
+// Geometries that need an 8-CTA cluster of the 256-thread build CAN go to the 512-thread build (clusters of 4).
+// Measured at BASELINE config 2: in isolation (scripts/time_pool2.py) forward 0.514 -> 0.526 ms (its chains have
+// nothing to hide behind when the CTA is alone on its SM: the gain of 37 instead of 33 capsules in flight is
+// spent on them), backward 1.134 -> 1.124 ms plain, 1.188 -> 1.176 ms pre-split; inside the training step
+// (bench.py) the backward measures the same either way (1.196 vs 1.197 ms).  So the 256-thread build stays
+// the default and the 512-thread one is opt-in:
+// QEC_FUSED_WIDE = 0 (never, default) | 1 (both) | f (forward only) | b (backward only).
+static int g_wide_mode = [] {  // 0 never | 1 both | 2 forward only | 3 backward only
+    const char* e = getenv("QEC_FUSED_WIDE");
+    const char c = (e != nullptr) ? e[0] : '0';
+    return c == '1' ? 1 : c == 'f' ? 2 : c == 'b' ? 3 : 0;
+}();
 static bool use_wide(long long J, bool backward) {
-    static const char mode = [] {
-        const char* e = getenv("QEC_FUSED_WIDE");
-        return (e != nullptr && e[0] != 0) ? e[0] : 'b';
-    }();
-    const bool on = mode == '1' || (backward ? mode == 'b' : mode == 'f');
+    const int m = g_wide_mode;
+    const bool on = m == 1 || (backward ? m == 3 : m == 2);
     return on && pick_cluster((int)J) == 8;
+}
+// select the build at run time (tests, A/B timing); returns the previous mode
+extern "C" int qec_routing_fused_set_wide(int mode) {
+    const int prev = g_wide_mode;
+    if (mode >= 0 && mode <= 3) g_wide_mode = mode;
+    return prev;
 }
 
 // 1 if the packed-pair kernels serve this geometry (callers normally just call qec_routing_fused_*,

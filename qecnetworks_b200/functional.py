@@ -128,6 +128,11 @@ class Routing(torch.autograd.Function):
         return g_votes, g_act, g_ab[0:1], g_ab[1:2], None
 
 
+def set_fused_wide(mode):
+    """0 | 1 | 2 | 3, see qec_routing_fused_set_wide in include/qec_b200.h; returns the previous mode"""
+    return _lib.query("qec_routing_fused_set_wide", int(mode))
+
+
 def routing_fused_forward_raw(t_oqi, lrfs, activation, alpha, beta, T):
     """no autograd: -> pose, agreement, poses_all [T,B,P,O,4], stats [B,P,O,2] (the last two are what
     the backward needs besides the inputs)"""

@@ -15,3 +15,19 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture
+def fused_build():
+    """select the build of the packed cluster kernels for one test (0 = 256 threads / clusters of 8, 1 = 512
+    threads / clusters of 4, see qec_routing_fused_set_wide) and restore the previous choice afterwards"""
+    from qecnetworks_b200 import functional as QF
+
+    prev = []
+
+    def select(mode):
+        prev.append(QF.set_fused_wide(mode))
+
+    yield select
+    if prev:
+        QF.set_fused_wide(prev[0])

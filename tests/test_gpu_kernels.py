@@ -312,8 +312,13 @@ def _oqi_perm(I, O):
         (2, 1, 129, 128, 2, 2),   # J = 16512: just above two full 8 192-vote CTAs, last CTA nearly empty
     ],
 )
-def test_routing_fused(B, P, K, I, O, T):
+@pytest.mark.parametrize("wide", [0, 1])
+def test_routing_fused(B, P, K, I, O, T, wide, fused_build):
     from qecnetworks_b200 import functional as QF
+
+    if wide and K * I <= 16384:
+        pytest.skip("the 512-thread build only serves capsules of more than 16 384 votes")
+    fused_build(wide)
 
     dev = cuda()
     assert QF.routing_fused_supported(K, I, O, T)
@@ -390,13 +395,17 @@ def test_routing_fused(B, P, K, I, O, T):
         (1, 1, 1, 2, 1, 3),       # a single pair, one of its votes dead
     ],
 )
-def test_routing_fused_packed_vs_scalar_and_split(B, P, K, I, O, T):
+@pytest.mark.parametrize("wide", [0, 1])
+def test_routing_fused_packed_vs_scalar_and_split(B, P, K, I, O, T, wide, fused_build):
     """the packed-pair kernels (routing_fused2.cu) against the scalar ones (routing_fused.cu) through the
     C ABI on the same inputs, incl. a capsule with a single live vote (|<pose, vote>| = 1: the distance
     gradient is infinite there and must be selected away, not multiplied by zero); and the pre-split
     gradient of qec_routing_fused_bwd_split: hi on the TF32 grid, hi + lo == g bit-exactly"""
     from qecnetworks_b200 import functional as QF, _lib
 
+    if wide and K * I <= 16384:
+        pytest.skip("the 512-thread build only serves capsules of more than 16 384 votes")
+    fused_build(wide)
     dev = cuda()
     assert QF.routing_fused_packed_supported(K, I, O, T)
     gen = torch.Generator().manual_seed(K * 3 + I)
