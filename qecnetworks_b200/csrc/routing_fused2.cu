@@ -1128,7 +1128,7 @@ static int pick_cluster_wide(long long J) {
         default: return FN<4>(__VA_ARGS__);    \
     }
 
-extern "C" int qec_fused2_wide_fwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
+extern "C" __attribute__((visibility("hidden"))) int qec_fused2_wide_fwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
                                    const float* beta, float* pose, float* agreement, float* poses_all, float* stats,
                                    int BP, int K, int I, int O, int T, void* stream) {
     const int CL = pick_cluster_wide((long long)K * I);
@@ -1139,7 +1139,7 @@ extern "C" int qec_fused2_wide_fwd(const float* t_oqi, const float* lrfs, const 
                          O, T, st)
 }
 
-extern "C" int qec_fused2_wide_bwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
+extern "C" __attribute__((visibility("hidden"))) int qec_fused2_wide_bwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
                                    const float* beta, const float* poses_all, const float* stats, const float* g_pose,
                                    const float* g_agreement, float* g_toqi, unsigned short* g_lo, float* g_lrfs,
                                    float* g_act, float* g_alpha_beta, int BP, int K, int I, int O, int T, void* stream) {
@@ -1153,10 +1153,10 @@ extern "C" int qec_fused2_wide_bwd(const float* t_oqi, const float* lrfs, const 
 
 #else  // ---------------- the 256-thread build owns the public entry points ----------------
 
-extern "C" int qec_fused2_wide_fwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
+extern "C" __attribute__((visibility("hidden"))) int qec_fused2_wide_fwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
                                    const float* beta, float* pose, float* agreement, float* poses_all, float* stats,
                                    int BP, int K, int I, int O, int T, void* stream);
-extern "C" int qec_fused2_wide_bwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
+extern "C" __attribute__((visibility("hidden"))) int qec_fused2_wide_bwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
                                    const float* beta, const float* poses_all, const float* stats, const float* g_pose,
                                    const float* g_agreement, float* g_toqi, unsigned short* g_lo, float* g_lrfs,
                                    float* g_act, float* g_alpha_beta, int BP, int K, int I, int O, int T, void* stream);

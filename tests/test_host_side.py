@@ -32,6 +32,12 @@ def test_library_exports_every_declared_symbol():
         assert n in _lib.SIGNATURES, n
     assert set(_lib.SIGNATURES) == set(names)
     assert lib.qec_b200_version() == 100
+    # ... and nothing undeclared: every qec_* function the library exports is part of the documented C ABI
+    import subprocess
+
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln and ln.split()[-1].startswith("qec_")}
+    assert exported <= set(names) | {"qec_prof_read"}, exported - set(names)  # (qec_prof_read: -DQEC_PROF builds only)
 
 
 def test_argument_validation_without_gpu():
