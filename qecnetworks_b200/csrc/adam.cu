@@ -7,26 +7,10 @@
 // and the zeroing of the gradient buffer for the next step.
 //
 // CUDA-graph friendly: the step counter lives on the device; the last block to finish advances it.
+#include "adam_math.cuh"
 #include "qec_common.cuh"
 
 namespace qec {
-
-struct AdamHyper {
-    double beta1_d, beta2_d;  // for the bias corrections, which torch evaluates in double
-    float lr, beta1, beta2, omb1, omb2, eps, weight_decay, grad_scale;  // omb = 1 - beta, rounded from double
-    int zero_grad;
-};
-
-__device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v, const AdamHyper& h, float inv_bc1,
-                                         float inv_sqrt_bc2) {
-    float gr = g * h.grad_scale;
-    if (h.weight_decay != 0.f) gr = fmaf(h.weight_decay, p, gr);  // L2 penalty folded into the gradient (torch.optim.Adam)
-    m = fmaf(h.beta1, m, h.omb1 * gr);
-    v = fmaf(h.beta2, v, h.omb2 * gr * gr);
-    const float denom = fmaf(sqrtf(v), inv_sqrt_bc2, h.eps);
-    p -= (h.lr * inv_bc1) * (m / denom);
-    if (h.zero_grad) g = 0.f;
-}
 
 // state: [0] = steps taken so far (as int), [1] = blocks finished in this launch
 __global__ void __launch_bounds__(256)
@@ -35,11 +19,7 @@ __global__ void __launch_bounds__(256)
     // bias corrections 1 - beta^t in double like torch.optim.Adam (1 - 0.999f loses five digits at t = 1):
     // one thread per block evaluates them, 2 x pow is ~1 us of latency
     __shared__ float bc[2];
-    if (threadIdx.x == 0) {
-        const double t = (double)(state[0] + 1);
-        bc[0] = (float)(1.0 / (1.0 - pow(h.beta1_d, t)));
-        bc[1] = (float)(1.0 / sqrt(1.0 - pow(h.beta2_d, t)));
-    }
+    if (threadIdx.x == 0) adam_bias_corrections(h, state[0] + 1, bc[0], bc[1]);
     __syncthreads();
     const float inv_bc1 = bc[0], inv_sqrt_bc2 = bc[1];
     const long long n4 = n >> 2;
@@ -86,8 +66,7 @@ extern "C" int qec_adam_flat(float* params, float* grads, float* exp_avg, float*
     QEC_CHECK_ARG(state, 13);
     QEC_CHECK_ARG(((reinterpret_cast<size_t>(params) | reinterpret_cast<size_t>(grads) | reinterpret_cast<size_t>(exp_avg) |
                     reinterpret_cast<size_t>(exp_avg_sq)) & 15) == 0, 1);
-    qec::AdamHyper h{beta1, beta2, lr, (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), eps, weight_decay,
-                     grad_scale, zero_grad};
+    const qec::AdamHyper h = qec::adam_hyper(lr, beta1, beta2, eps, weight_decay, grad_scale, zero_grad);
     long long blocks = ((n >> 2) + 255) / 256;
     if (blocks < 1) blocks = 1;
     if (blocks > 4 * qec::kNumSMs) blocks = 4 * qec::kNumSMs;

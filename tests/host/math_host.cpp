@@ -1,5 +1,6 @@
 // Host build of qec_math.cuh for CPU-side unit tests (test scaffolding only).
 #include "../../qecnetworks_b200/csrc/qec_math.cuh"
+#include "../../qecnetworks_b200/csrc/adam_math.cuh"
 
 using namespace qec;
 
@@ -86,6 +87,20 @@ void h_qrotv(int n, const float* q, const float* v, const float* g, float* x, fl
         qrotv_bwd(qq, vv, gg, a, b);
         gq[4 * i] = a.w; gq[4 * i + 1] = a.x; gq[4 * i + 2] = a.y; gq[4 * i + 3] = a.z;
         gv[3 * i] = b.x; gv[3 * i + 1] = b.y; gv[3 * i + 2] = b.z;
+    }
+}
+
+// `steps` Adam steps on n elements with the element update and bias corrections of qec_adam_flat; grads: [steps][n]
+void h_adam_steps(int n, int steps, float* p, const float* grads, float* m, float* v, float lr, double beta1, double beta2,
+                  float eps, float weight_decay, float grad_scale) {
+    const AdamHyper h = adam_hyper(lr, beta1, beta2, eps, weight_decay, grad_scale, 0);
+    for (int t = 1; t <= steps; ++t) {
+        float c1, c2;
+        adam_bias_corrections(h, t, c1, c2);
+        for (int i = 0; i < n; ++i) {
+            float g = grads[(size_t)(t - 1) * n + i];
+            adam_one(p[i], g, m[i], v[i], h, c1, c2);
+        }
     }
 }
 }

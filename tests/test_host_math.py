@@ -163,3 +163,30 @@ def test_qrotv_and_adjoint(lib):
     assert np.abs(x - xr.detach().numpy()).max() < 2e-5
     assert np.abs(gq - qt.grad.numpy()).max() < 2e-5
     assert np.abs(gv - vt.grad.numpy()).max() < 2e-5
+
+
+@pytest.mark.parametrize("weight_decay,scale", [(0.0, 1.0), (0.01, 0.125)])
+def test_adam_element_update_matches_torch_adam(lib, weight_decay, scale):
+    """csrc/adam_math.cuh (the element update and the double-precision bias corrections of qec_adam_flat) against
+    torch.optim.Adam -- the optimizer of the reference's train_cls.py:44-51 -- over 25 steps with gradients
+    spanning five decades"""
+    n, steps = 1003, 25
+    g = torch.Generator().manual_seed(4)
+    p0 = torch.randn(n, generator=g)
+    grads = torch.stack([torch.randn(n, generator=g) * (10.0 ** (t % 5 - 2)) for t in range(steps)])
+    q = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([q], lr=1e-3, weight_decay=weight_decay)
+    for t in range(steps):
+        q.grad = grads[t].clone()
+        opt.step()
+    p = p0.numpy().copy()
+    m = np.zeros(n, dtype=np.float32)
+    v = np.zeros(n, dtype=np.float32)
+    gin = np.ascontiguousarray((grads / scale).numpy())  # the kernel reads grad * grad_scale
+    lib.h_adam_steps.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4 + [
+        ctypes.c_float, ctypes.c_double, ctypes.c_double, ctypes.c_float, ctypes.c_float, ctypes.c_float]
+    lib.h_adam_steps(n, steps, P(p), P(gin), P(m), P(v), 1e-3, 0.9, 0.999, 1e-8, weight_decay, scale)
+    st = opt.state[q]
+    assert np.abs(p - q.detach().numpy()).max() <= 2e-6 * max(1.0, float(q.detach().abs().max()))
+    assert np.abs(m - st["exp_avg"].numpy()).max() <= 1e-6 * max(1.0, float(st["exp_avg"].abs().max()))
+    assert np.abs(v - st["exp_avg_sq"].numpy()).max() <= 1e-6 * max(1.0, float(st["exp_avg_sq"].abs().max()))
