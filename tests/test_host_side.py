@@ -205,3 +205,24 @@ def test_flat_adam_host_layout_and_no_cpu_fallback():
     assert bucket.params[0] is next(net.pool2.parameters())
     with pytest.raises(_lib.QecLibraryError):
         opt.step()
+
+
+def test_fused_build_selector_without_gpu():
+    """qec_routing_fused_set_wide: returns the previous mode, ignores out-of-range values (query only); the
+    default is the 256-thread build unless QEC_FUSED_WIDE says otherwise"""
+    from qecnetworks_b200 import _lib
+
+    lib = _lib.load()
+    start = lib.qec_routing_fused_set_wide(-1)
+    assert start in (0, 1, 2, 3)
+    if "QEC_FUSED_WIDE" not in os.environ:
+        assert start == 0
+    try:
+        assert lib.qec_routing_fused_set_wide(3) == start
+        assert lib.qec_routing_fused_set_wide(99) == 3   # out of range: unchanged
+        assert lib.qec_routing_fused_set_wide(1) == 3
+        # argument validation happens before the build is chosen: no launch without a GPU either way
+        assert lib.qec_routing_fused_fwd(None, None, None, None, None, None, None, None, None, 1, 256, 128, 4, 3, None) == -1
+    finally:
+        lib.qec_routing_fused_set_wide(start)
+    assert lib.qec_routing_fused_set_wide(-1) == start
