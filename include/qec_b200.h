@@ -10,9 +10,13 @@
  * Conventions
  *  - every pointer is a DEVICE pointer to contiguous FP32 (int64 / int32 where
  *    stated) on the current device; quaternions are (w,x,y,z), 16-byte aligned;
- *  - the caller owns and allocates every buffer; the library never allocates,
- *    never synchronises and keeps no global mutable state, so it is re-entrant
- *    (one thread per GPU under DataParallel, one process per GPU under DDP);
+ *  - the caller owns and allocates every buffer; the library never allocates and
+ *    never synchronises.  Its only process-wide state is launch configuration
+ *    (occupancy / the shared-memory opt-in of the cluster kernels), cached PER
+ *    DEVICE ORDINAL in atomics, and the build selector of
+ *    qec_routing_fused_set_wide (an atomic), so it is re-entrant: one thread per
+ *    GPU under the reference's nn.DataParallel (the calling thread's current
+ *    device must be the device of the pointers), one process per GPU under DDP;
  *  - `stream` is a cudaStream_t (NULL = legacy default stream); all work is
  *    enqueued on it and is CUDA-graph capturable;
  *  - return value: 0 on success; -k if the k-th argument is invalid (mirrors
@@ -189,6 +193,21 @@ int qec_fold_chunks(const float* a, const float* b, const long long* perm, float
  * scatter_ raises). */
 int qec_spread_loss(const float* x, const long long* labels, float margin, float* loss, float* g_x, float* scratch,
                     int* err, int B, int C, void* stream);
+
+/* The losses of the two networks with their gradients in ONE launch: spread loss of S = 1
+ * (models/qec_net.py:53-59) or S = 2 branches (models/qec_sia_net.py:69-77) plus, if pose != NULL, w_pose times the
+ * pose-difference loss (qec_sia_net.py:79-82) on the poses of the ground-truth class, i.e. including the per-sample
+ * selection loop of train_cls_sia.py:72-78 (pose_out_act[:, i] = pose_out[:, i, y_i]).
+ *   x [S,B,C] (NULL with S = 0: pose term only), labels [B] int64, pose [2,B,C,4] | NULL
+ *   -> loss [3] = {total, spread, pose_diff}, g_x [S,B,C], g_pose [2,B,C,4] | NULL (zero off the label class).
+ * err: device int set to 1 if a label is outside [0, C). */
+int qec_class_pose_loss(const float* x, const long long* labels, float margin, const float* pose, float w_pose,
+                        float* loss, float* g_x, float* g_pose, int* err, int S, int B, int C, void* stream);
+
+/* Evaluation-side quaternion ops of test_rot_sia.py, batched: pose1, pose2 [n,4] ->
+ * dist [n] | NULL = (2/pi) acos(min(|<fix(p1), fix(p2)>|, 1)) (q_distance, test_rot_sia.py:32-41),
+ * rel [n,4] | NULL = conj(pose1) (x) pose2 (the relative pose, test_rot_sia.py:131-132). */
+int qec_quat_eval(const float* pose1, const float* pose2, float* dist, float* rel, long long n, void* stream);
 
 /* Which build of the packed cluster-resident routing kernels serves capsules of more than 16 384 votes:
  * 0 = 256 threads per CTA, two CTAs per SM, clusters of 8 (default); 1 = 512 threads, one CTA per SM, clusters

@@ -119,6 +119,12 @@ def symeig_rows_backward(gw, gV_rows, w, V_rows):
 
 _SAFE_DIAG = (1.0, 2.0, 3.0, 4.0)
 
+# The eigen-solver the restated QecModule calls at the reference's ``S.symeig`` call sites
+# (qec_module.py:52,90): [n,4,4] -> (w [n,4] ascending, V [n,4,4] rows = eigenvectors).  Tests may swap it
+# (tests/test_gpu_module.py runs this restatement of the reference loop on the GPU around
+# ``qecnetworks_b200.symeig``); the default is the LAPACK statement above.
+SYMEIG = symeig_rows
+
 
 def _masked_top(M, valid, noise=0.0, generator=None):
     """Top eigenvector (largest eigenvalue) of each valid 4x4, zeros elsewhere.
@@ -131,8 +137,8 @@ def _masked_top(M, valid, noise=0.0, generator=None):
     Ms = torch.where(valid[..., None, None], M, safe)
     if noise:
         Ms = Ms + noise * torch.randn(Ms.shape, dtype=Ms.dtype, generator=generator)
-    _, V = torch.linalg.eigh(Ms, UPLO="U")
-    return V[..., :, -1] * valid[..., None].to(M.dtype)
+    _, Vrows = SYMEIG(Ms.reshape(-1, 4, 4))
+    return Vrows[:, -1, :].reshape(M.shape[:-1]) * valid[..., None].to(M.dtype)
 
 
 # --------------------------------------------------------------------------

@@ -42,6 +42,8 @@ SIGNATURES = {
     "qec_split_operand": ([_P, _P, _F, _P, _P, _P, _LL, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], 1),
     "qec_fold_chunks": ([_P, _P, _P, _P, _P, _I, _LL, _I, _I, _I, _P], 1),
     "qec_spread_loss": ([_P, _P, _F, _P, _P, _P, _P, _I, _I, _P], 2),
+    "qec_class_pose_loss": ([_P, _P, _F, _P, _F, _P, _P, _P, _P, _I, _I, _I, _P], 1),
+    "qec_quat_eval": ([_P, _P, _P, _P, _LL, _P], 1),
     "qec_adam_flat": ([_P, _P, _P, _P, _LL, _F, _D, _D, _F, _F, _F, _I, _P, _P], 1),
     "qec_ffma_peak": ([_P, _I, _I, _P], 1),
     "qec_pipe_probe": ([_P, _I, _I, _I, _P], 1),
@@ -98,6 +100,34 @@ def call(name, *args):
             raise QecLibraryError("%s: argument %d is invalid" % (name, -rc))
         raise QecLibraryError("%s: CUDA error %d at launch" % (name, rc))
     _launches += SIGNATURES[name][1]
+
+
+def launch(name, *args):
+    """call() for tensor arguments: every torch tensor among `args` is passed as its device pointer (None as a
+    null pointer), all of them must live on ONE CUDA device, and the kernels are launched on THAT device's
+    current stream with that device made current for the call -- like a native PyTorch op, whatever
+    torch.cuda.current_device() happens to be (a module moved with net.to('cuda:1'), or the reference's
+    nn.DataParallel with one thread per GPU).  The stream is appended as the last argument."""
+    import torch
+
+    dev = None
+    raw = []
+    for i, a in enumerate(args):
+        if isinstance(a, torch.Tensor):
+            if not a.is_cuda:
+                raise QecLibraryError("%s: argument %d is a CPU tensor (the QEC kernels have no CPU implementation)"
+                                      % (name, i + 1))
+            if dev is None:
+                dev = a.device
+            elif a.device != dev:
+                raise QecLibraryError("%s: argument %d lives on %s, the others on %s" % (name, i + 1, a.device, dev))
+            raw.append(a.data_ptr())
+        else:
+            raw.append(a)
+    if dev is None:
+        raise QecLibraryError("%s: no tensor argument to take the device from" % name)
+    with torch.cuda.device(dev):
+        call(name, *raw, torch.cuda.current_stream(dev).cuda_stream)
 
 
 def query(name, *args):

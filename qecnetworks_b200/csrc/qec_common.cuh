@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "qec_math.cuh"
 
 namespace qec {
@@ -16,6 +18,25 @@ constexpr int kNumSMs = 148;
     do {                         \
         if (!(cond)) return -(idx); \
     } while (0)
+
+// Launch configuration that is expensive to query (occupancy) or has to be set once per DEVICE
+// (cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute): cached per device ordinal of the
+// calling thread's current device, so that one process driving several GPUs -- the reference's
+// nn.DataParallel, train_cls.py:27: one Python thread per GPU -- configures every one of them.
+// Relaxed atomics: two threads racing on one device both compute and store the same value.
+constexpr int kMaxDevices = 64;
+struct PerDeviceInt {
+    std::atomic<int> v[kMaxDevices];
+    PerDeviceInt() {
+        for (auto& x : v) x.store(-1, std::memory_order_relaxed);
+    }
+    // slot of the current device; nullptr (= do not cache) if the ordinal cannot be had or is out of range
+    std::atomic<int>* slot() {
+        int d = -1;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) return nullptr;
+        return &v[d];
+    }
+};
 
 inline int launch_status() {
     const cudaError_t e = cudaPeekAtLastError();

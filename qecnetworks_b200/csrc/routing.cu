@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(kGroupThreads)
     const long long c = active ? gid : Nc - 1;
     GroupCoop<G> coop;
     VotesCached vs{votes + (size_t)c * J * 4};
-    // tail lanes recompute the last capsule but must not store: point them at a dead sink
+    // tail lanes shadow the last capsule (warp-uniform control flow) and store the same g_votes values to the
+    // same addresses as its owner: a benign duplicate store, no separate sink
     SinkGlobal sink{g_votes + (size_t)c * J * 4};
     const float* act_row = act + (size_t)(c / O) * J;
     float* g_act_row = (g_act != nullptr && active) ? g_act + (size_t)(c / O) * J : nullptr;

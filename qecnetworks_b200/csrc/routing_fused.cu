@@ -490,7 +490,7 @@ static int launch_fused_fwd(const float* t_oqi, const float* lrfs, const float* 
     auto kern = routing_fused_fwd_kernel<CL>;
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
-    static int cached = -1;
+    static PerDeviceInt cached;
     const int rc = fused_grid(kern, CL, kFwdT, kFwdSmem, Nc, cfg, attr, cached);
     if (rc) return rc;
     cfg.stream = st;
@@ -507,7 +507,7 @@ static int launch_fused_bwd(const float* t_oqi, const float* lrfs, const float* 
     auto kern = routing_fused_bwd_kernel<CL>;
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
-    static int cached = -1;
+    static PerDeviceInt cached;
     const int rc = fused_grid(kern, CL, kBT, kBwdSmem, Nc, cfg, attr, cached);
     if (rc) return rc;
     cfg.stream = st;

@@ -541,7 +541,7 @@ constexpr size_t fwd2_smem() {
 // push reducer addresses its own CTA through the cluster window as well
 template <class Kern>
 static int fused2_grid(Kern kern, int CL, size_t smem, long long Nc, cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr,
-                       int& cached_clusters) {
+                       PerDeviceInt& cache) {
     cfg.blockDim = dim3(kPT);
     cfg.dynamicSmemBytes = smem;
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -550,7 +550,8 @@ static int fused2_grid(Kern kern, int CL, size_t smem, long long Nc, cudaLaunchC
     attr[0].val.clusterDim.z = 1;
     cfg.numAttrs = 1;
     cfg.attrs = attr;
-    int clusters = cached_clusters;
+    std::atomic<int>* slot = cache.slot();  // per device: the shared-memory opt-in below is a per-device attribute
+    int clusters = slot ? slot->load(std::memory_order_relaxed) : -1;
     if (clusters < 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
@@ -558,7 +559,7 @@ static int fused2_grid(Kern kern, int CL, size_t smem, long long Nc, cudaLaunchC
         e = cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg);
         if (e != cudaSuccess) return (int)e;
         if (clusters < 1) return (int)cudaErrorLaunchOutOfResources;
-        cached_clusters = clusters;
+        if (slot) slot->store(clusters, std::memory_order_relaxed);
     }
     if (clusters > Nc) clusters = (int)Nc;
     cfg.gridDim = dim3((unsigned)(clusters * CL));
@@ -572,7 +573,7 @@ static int launch_fused2_fwd(const float* t_oqi, const float* lrfs, const float*
     const bool full = ((long long)K * I == (long long)CL * 2 * kNpMax);
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
-    static int cached[2] = {-1, -1};
+    static PerDeviceInt cached[2];
     cudaError_t e;
     if (full) {
         auto kern = routing_fused2_fwd_kernel<CL, true>;
@@ -1081,7 +1082,7 @@ static int launch_fused2_bwd(const float* t_oqi, const float* lrfs, const float*
     const bool full = ((long long)K * I == (long long)CL * 2 * kNpMax);
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
-    static int cached[2] = {-1, -1};
+    static PerDeviceInt cached[2];
     cudaError_t e;
     if (full) {
         auto kern = routing_fused2_bwd_kernel<CL, true>;
@@ -1168,21 +1169,20 @@ extern "C" __attribute__((visibility("hidden"))) int qec_fused2_wide_bwd(const f
 // (bench.py) the backward measures the same either way (1.196 vs 1.197 ms).  So the 256-thread build stays
 // the default and the 512-thread one is opt-in:
 // QEC_FUSED_WIDE = 0 (never, default) | 1 (both) | f (forward only) | b (backward only).
-static int g_wide_mode = [] {  // 0 never | 1 both | 2 forward only | 3 backward only
+static std::atomic<int> g_wide_mode{[] {  // 0 never | 1 both | 2 forward only | 3 backward only
     const char* e = getenv("QEC_FUSED_WIDE");
     const char c = (e != nullptr) ? e[0] : '0';
     return c == '1' ? 1 : c == 'f' ? 2 : c == 'b' ? 3 : 0;
-}();
+}()};
 static bool use_wide(long long J, bool backward) {
-    const int m = g_wide_mode;
+    const int m = g_wide_mode.load(std::memory_order_relaxed);
     const bool on = m == 1 || (backward ? m == 3 : m == 2);
     return on && pick_cluster((int)J) == 8;
 }
 // select the build at run time (tests, A/B timing); returns the previous mode
 extern "C" int qec_routing_fused_set_wide(int mode) {
-    const int prev = g_wide_mode;
-    if (mode >= 0 && mode <= 3) g_wide_mode = mode;
-    return prev;
+    if (mode >= 0 && mode <= 3) return g_wide_mode.exchange(mode, std::memory_order_relaxed);
+    return g_wide_mode.load(std::memory_order_relaxed);
 }
 
 // 1 if the packed-pair kernels serve this geometry (callers normally just call qec_routing_fused_*,

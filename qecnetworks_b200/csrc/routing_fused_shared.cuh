@@ -119,7 +119,7 @@ __device__ __forceinline__ Quat solve_pose(const float* acc, bool valid) {
 // persistent grid: as many clusters as can be co-resident, never more than there are capsules
 template <class Kern>
 static int fused_grid(Kern kern, int CL, int threads, size_t smem, long long Nc, cudaLaunchConfig_t& cfg,
-                      cudaLaunchAttribute* attr, int& cached_clusters) {
+                      cudaLaunchAttribute* attr, PerDeviceInt& cache) {
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.numAttrs = 0;
@@ -131,7 +131,8 @@ static int fused_grid(Kern kern, int CL, int threads, size_t smem, long long Nc,
         attr[0].val.clusterDim.z = 1;
         cfg.numAttrs = 1;
     }
-    int clusters = cached_clusters;  // per kernel instantiation; every B200 gives the same answer
+    std::atomic<int>* slot = cache.slot();  // per kernel instantiation AND per device (the opt-in below is per device)
+    int clusters = slot ? slot->load(std::memory_order_relaxed) : -1;
     if (clusters < 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
@@ -146,7 +147,7 @@ static int fused_grid(Kern kern, int CL, int threads, size_t smem, long long Nc,
             clusters = per_sm * kNumSMs;
         }
         if (clusters < 1) return (int)cudaErrorLaunchOutOfResources;
-        cached_clusters = clusters;
+        if (slot) slot->store(clusters, std::memory_order_relaxed);
     }
     if (clusters > Nc) clusters = (int)Nc;
     cfg.gridDim = dim3((unsigned)(clusters * CL));

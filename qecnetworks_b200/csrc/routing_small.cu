@@ -261,14 +261,15 @@ static int small_kmax(int K) { return K <= 9 ? 9 : (K <= 16 ? 16 : 0); }
 
 // persistent grid: exactly as many CTAs as are co-resident (one wave), each walking over many patches
 template <class Kern>
-static dim3 small_grid(Kern kern, int BP, int O, int& cached_per_sm) {
+static dim3 small_grid(Kern kern, int BP, int O, PerDeviceInt& cache) {
     const int gy = (O + kST - 1) / kST;
-    if (cached_per_sm < 0) {
-        int per_sm = 0;
+    std::atomic<int>* slot = cache.slot();
+    int per_sm = slot ? slot->load(std::memory_order_relaxed) : -1;
+    if (per_sm < 0) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kST, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
-        cached_per_sm = per_sm;
+        if (slot) slot->store(per_sm, std::memory_order_relaxed);
     }
-    int gx = (kNumSMs * cached_per_sm) / gy;
+    int gx = (kNumSMs * per_sm) / gy;
     if (gx < 1) gx = 1;
     if (gx > BP) gx = BP;
     return dim3((unsigned)gx, (unsigned)gy);
@@ -295,7 +296,7 @@ extern "C" int qec_routing_small_fwd(const float* xrot, const float* lrfs, const
     QEC_CHECK_ARG(BP > 0, 12);
     QEC_CHECK_ARG(qec_routing_small_supported(K, 1, O, T), 13);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    static int occ9 = -1, occ16 = -1;
+    static PerDeviceInt occ9, occ16;
     const dim3 grid = (small_kmax(K) == 9) ? small_grid(routing_small_fwd_kernel<9>, BP, O, occ9)
                                            : small_grid(routing_small_fwd_kernel<16>, BP, O, occ16);
     if (small_kmax(K) == 9)
@@ -320,7 +321,7 @@ extern "C" int qec_routing_small_bwd(const float* xrot, const float* lrfs, const
     QEC_CHECK_ARG(BP > 0, 15);
     QEC_CHECK_ARG(qec_routing_small_supported(K, 1, O, T), 16);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    static int occ9 = -1, occ16 = -1;
+    static PerDeviceInt occ9, occ16;
     const dim3 grid = (small_kmax(K) == 9) ? small_grid(routing_small_bwd_kernel<9>, BP, O, occ9)
                                            : small_grid(routing_small_bwd_kernel<16>, BP, O, occ16);
     if (small_kmax(K) == 9)

@@ -45,11 +45,23 @@ class FlatGradBucket:
     in the buffer and their slice is all-reduced ASYNCHRONOUSLY as soon as the last of them has been
     accumulated (post-accumulate-grad hooks), so the transfer overlaps the rest of the backward instead
     of being exposed at the end of the step; all_reduce_mean() then reduces the small remainder and
-    joins.  Every rank launches the same two collectives in the same order.  Protocol per step:
-    zero() -> forward -> backward -> all_reduce_mean(); a backward that is NOT followed by
-    all_reduce_mean() must run with `overlap = False`."""
+    joins.
 
-    def __init__(self, params, early=None):
+    Collective order is the same on every rank by construction: with `early` parameters a step always
+    issues exactly two all-reduces on `group`, the early slice first and the remainder second.  If the
+    hooks of a rank did not all fire during its backward (an early parameter without a gradient in that
+    step), all_reduce_mean() issues the early slice itself before the remainder -- late, but in the same
+    order, so the ranks cannot mismatch.
+
+    The gradients must stay views of the flat buffer: `optimizer.zero_grad()` of torch optimizers defaults
+    to set_to_none=True, which drops the views (autograd would then allocate fresh `.grad` tensors and the
+    all-reduce would see a stale buffer).  Use `bucket.zero()` (or `zero_grad(set_to_none=False)`);
+    all_reduce_mean() checks the aliasing and raises otherwise.
+
+    Protocol per step: zero() -> forward -> backward -> all_reduce_mean(); a backward that is NOT
+    followed by all_reduce_mean() must run with `overlap = False`."""
+
+    def __init__(self, params, early=None, group=None):
         params = [p for p in params if p.requires_grad]
         if not params:
             raise ValueError("no trainable parameters")
@@ -60,13 +72,15 @@ class FlatGradBucket:
         n = sum(p.numel() for p in self.params)
         self.n_early = sum(p.numel() for p in self.early)
         self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
+        self._views = []
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self._views.append((p, off))
             off += p.numel()
         self._seen = 0
         self._work = None
-        self._group = None
+        self._group = group  # fixed at construction: the hooks and all_reduce_mean() use the same one
         self.overlap = True  # set to False for a backward pass that must not touch the network (no all_reduce_mean after it)
         for p in self.early:
             p.register_post_accumulate_grad_hook(self._on_early_grad)
@@ -82,6 +96,17 @@ class FlatGradBucket:
                 self._work = dist.all_reduce(self.flat[:self.n_early], op=dist.ReduceOp.SUM, group=self._group,
                                              async_op=True)
 
+    def check_views(self):
+        """every parameter's .grad is still the view of the flat buffer it was given"""
+        base = self.flat.data_ptr()
+        for p, off in self._views:
+            g = p.grad
+            if g is None or g.data_ptr() != base + 4 * off or g.numel() != p.numel():
+                raise RuntimeError(
+                    "FlatGradBucket: a parameter's .grad no longer aliases the flat gradient buffer (was "
+                    "optimizer.zero_grad() called with set_to_none=True?): use bucket.zero() or "
+                    "zero_grad(set_to_none=False), otherwise the all-reduce would exchange a stale buffer")
+
     def zero(self):
         if self._work is not None:  # a reduction nobody joined: finish it before the buffer is reused
             self._work.wait()
@@ -92,18 +117,30 @@ class FlatGradBucket:
     def all_reduce_mean(self, group=None, average=True):
         """sum over ranks / world size: the loss is a mean over the GLOBAL batch.  With average=False the
         division is left to the consumer (FlatAdam reads the gradient times 1/world); returns the factor
-        that is still owed (1.0 if nothing is)."""
-        self._group = group
+        that is still owed (1.0 if nothing is).  `group` is accepted for compatibility and must be the
+        group given at construction."""
+        if group is not None and group is not self._group:
+            raise ValueError("FlatGradBucket: pass the process group at construction (the overlap hooks use it)")
+        self.check_views()
+        group = self._group
         owed = 1.0
+        self._seen = 0
         if self._distributed():
             world = dist.get_world_size(group)
-            if self._work is not None:  # the early slice is already in flight
-                if self.n_early < self.flat.numel():
-                    dist.all_reduce(self.flat[self.n_early:], op=dist.ReduceOp.SUM, group=group)
+            if self.early and self.n_early < self.flat.numel():
+                # always two collectives, in this order, on every rank
+                if self._work is None:  # the hooks did not all fire on this rank (or overlap is off)
+                    self._work = dist.all_reduce(self.flat[:self.n_early], op=dist.ReduceOp.SUM, group=group,
+                                                 async_op=True)
+                dist.all_reduce(self.flat[self.n_early:], op=dist.ReduceOp.SUM, group=group)
                 self._work.wait()
                 self._work = None
             else:
-                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+                if self._work is not None:  # every parameter is "early": the one collective is in flight
+                    self._work.wait()
+                    self._work = None
+                else:
+                    dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
             if average:
                 self.flat.div_(world)
             else:
@@ -142,14 +179,12 @@ class FlatAdam:
 
     def step(self, grad_scale=1.0):
         from . import _lib
-        from ._lib import ptr
-        from .functional import _stream
 
         if not self.flat.is_cuda:
             raise _lib.QecLibraryError("FlatAdam.step: CUDA tensors only (no CPU fallback)")
-        _lib.call("qec_adam_flat", ptr(self.flat), ptr(self.bucket.flat), ptr(self.exp_avg), ptr(self.exp_avg_sq),
-                  self.flat.numel(), self.lr, float(self.betas[0]), float(self.betas[1]), self.eps, self.weight_decay,
-                  float(grad_scale), 1 if self.zero_grad else 0, ptr(self.state), _stream())
+        _lib.launch("qec_adam_flat", self.flat, self.bucket.flat, self.exp_avg, self.exp_avg_sq,
+                    self.flat.numel(), self.lr, float(self.betas[0]), float(self.betas[1]), self.eps, self.weight_decay,
+                    float(grad_scale), 1 if self.zero_grad else 0, self.state)
 
     def steps_taken(self):
         return int(self.state[0].item())

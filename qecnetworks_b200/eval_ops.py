@@ -21,20 +21,26 @@ def ave_pose(pose):
     return mean.view(B, 4)
 
 
-def _fix(q):
-    return q * torch.sign(q[..., :1])
-
-
 def q_distance(pose1, pose2):
-    """reference test_rot_sia.py:32-41: (2/pi) acos(min(|<fix(p1), fix(p2)>|, 1)); any leading batch shape"""
-    d = (_fix(pose1) * _fix(pose2)).sum(-1).abs().clamp(max=1.0)
-    return 2.0 * torch.acos(d) / math.pi
+    """reference test_rot_sia.py:32-41: (2/pi) acos(min(|<fix(p1), fix(p2)>|, 1)); any leading batch shape;
+    one launch (qec_quat_eval)"""
+    return QF.quat_eval(pose1.float(), pose2.float(), want_rel=False)[0]
 
 
 def relative_pose(pose1, pose2):
-    """conj(pose1) (x) pose2, the relative rotation the reference evaluates (test_rot_sia.py:131-132)"""
-    conj = pose1 * pose1.new_tensor([1.0, -1.0, -1.0, -1.0])
-    w1, x1, y1, z1 = conj.unbind(-1)
-    w2, x2, y2, z2 = pose2.unbind(-1)
-    return torch.stack([w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2, w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2,
-                        w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2, w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2], -1)
+    """conj(pose1) (x) pose2, the relative rotation the reference evaluates (test_rot_sia.py:131-132);
+    one launch (qec_quat_eval)"""
+    return QF.quat_eval(pose1.float(), pose2.float(), want_dist=False)[1]
+
+
+def relative_rotation_error(pose_out, labels, rot_gt):
+    """The rotation-error metric of the reference's Siamese test (test_rot_sia.py:94-123) on a batch, without the
+    per-sample Python loop: pose_out [2,B,C,4] (QecSiaNet output), labels [B] (the class whose capsule is read:
+    the prediction in the reference's test, the ground truth during training), rot_gt [B,4] = the rotation that
+    took branch 0 to branch 1.  Returns d [B] = q_distance(pose_0, conj(rot_gt) (x) pose_1): 0 when the network's
+    pose of branch 1 is exactly the rotated pose of branch 0."""
+    S, B, C, _ = pose_out.shape
+    idx = labels.view(1, B, 1, 1).expand(2, B, 1, 4).to(pose_out.device)
+    sel = pose_out.float().gather(2, idx).squeeze(2)          # [2, B, 4]
+    back = relative_pose(rot_gt.to(pose_out.device).float(), sel[1])  # conj(rot_gt) (x) pose_1
+    return q_distance(sel[0].contiguous(), back)

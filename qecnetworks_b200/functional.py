@@ -8,11 +8,7 @@ Tensors follow the reference layouts (models/qec_module.py):
 import torch
 
 from . import _lib
-from ._lib import call, ptr
-
-
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+from ._lib import launch
 
 
 def _check(t, name, shape=None):
@@ -40,7 +36,7 @@ class LrfMeanRotate(torch.autograd.Function):
         points = _check(points, "points", (B, P, K, 3))
         mean = torch.empty(B, P, I, 4, device=lrfs.device, dtype=torch.float32)
         xrot = torch.empty(B, P, K, I, 3, device=lrfs.device, dtype=torch.float32)
-        call("qec_lrf_mean_fwd", ptr(lrfs), ptr(activation), ptr(points), ptr(mean), ptr(xrot), B * P, K, I, _stream())
+        launch("qec_lrf_mean_fwd", lrfs, activation, points, mean, xrot, B * P, K, I)
         ctx.save_for_backward(lrfs, points, mean)
         return mean, xrot
 
@@ -55,8 +51,8 @@ class LrfMeanRotate(torch.autograd.Function):
         g_mean = None if g_mean is None else g_mean.contiguous()
         g_lrfs = torch.empty_like(lrfs)
         g_points = torch.zeros_like(points) if need_points else None
-        call("qec_lrf_mean_bwd", ptr(lrfs), ptr(points), ptr(mean), ptr(g_xrot), ptr(g_mean), ptr(g_lrfs),
-             ptr(g_points), B * P, K, I, _stream())
+        launch("qec_lrf_mean_bwd", lrfs, points, mean, g_xrot, g_mean, g_lrfs,
+             g_points, B * P, K, I)
         return (g_lrfs if need_lrfs else None), None, g_points
 
 
@@ -71,7 +67,7 @@ class Votes(torch.autograd.Function):
         lrfs = _check(lrfs, "lrfs", (B, P, K, I, 4))
         t_raw = _check(t_raw, "t_raw", (B * P * K, 4 * I * O))
         votes = torch.empty(B, P, O, K * I, 4, device=lrfs.device, dtype=torch.float32)
-        call("qec_votes_fwd", ptr(lrfs), ptr(t_raw), ptr(votes), B * P, K, I, O, _stream())
+        launch("qec_votes_fwd", lrfs, t_raw, votes, B * P, K, I, O)
         ctx.save_for_backward(lrfs, t_raw)
         return votes
 
@@ -84,7 +80,7 @@ class Votes(torch.autograd.Function):
         g_votes = g_votes.contiguous()
         g_traw = torch.empty_like(t_raw)
         g_lrfs = torch.zeros_like(lrfs) if need_lrfs else None
-        call("qec_votes_bwd", ptr(lrfs), ptr(t_raw), ptr(g_votes), ptr(g_traw), ptr(g_lrfs), B * P, K, I, O, _stream())
+        launch("qec_votes_bwd", lrfs, t_raw, g_votes, g_traw, g_lrfs, B * P, K, I, O)
         return g_lrfs, g_traw
 
 
@@ -106,8 +102,8 @@ class Routing(torch.autograd.Function):
         agreement = torch.empty(B, P, O, device=dev, dtype=torch.float32)
         poses_all = torch.empty(T, B, P, O, 4, device=dev, dtype=torch.float32)
         stats = torch.empty(B, P, O, 2, device=dev, dtype=torch.float32)
-        call("qec_routing_fwd", ptr(votes), ptr(activation), ptr(alpha), ptr(beta), ptr(pose), ptr(agreement),
-             ptr(poses_all), ptr(stats), B * P, O, J, T, _stream())
+        launch("qec_routing_fwd", votes, activation, alpha, beta, pose, agreement,
+             poses_all, stats, B * P, O, J, T)
         ctx.save_for_backward(votes, activation, alpha, beta, poses_all, stats)
         ctx.T = T
         return pose, agreement
@@ -123,8 +119,8 @@ class Routing(torch.autograd.Function):
         g_votes = torch.empty_like(votes)
         g_act = torch.zeros_like(activation) if need_act else None
         g_ab = torch.zeros(2, device=dev, dtype=torch.float32)
-        call("qec_routing_bwd", ptr(votes), ptr(activation), ptr(alpha), ptr(beta), ptr(poses_all), ptr(stats),
-             ptr(g_pose), ptr(g_agreement), ptr(g_votes), ptr(g_act), ptr(g_ab), B * P, O, J, ctx.T, _stream())
+        launch("qec_routing_bwd", votes, activation, alpha, beta, poses_all, stats,
+             g_pose, g_agreement, g_votes, g_act, g_ab, B * P, O, J, ctx.T)
         return g_votes, g_act, g_ab[0:1], g_ab[1:2], None
 
 
@@ -148,8 +144,8 @@ def routing_fused_forward_raw(t_oqi, lrfs, activation, alpha, beta, T):
     agreement = torch.empty(B, P, O, device=dev, dtype=torch.float32)
     poses_all = torch.empty(T, B, P, O, 4, device=dev, dtype=torch.float32)
     stats = torch.empty(B, P, O, 2, device=dev, dtype=torch.float32)
-    call("qec_routing_fused_fwd", ptr(t_oqi), ptr(lrfs), ptr(activation), ptr(alpha), ptr(beta), ptr(pose),
-         ptr(agreement), ptr(poses_all), ptr(stats), B * P, K, I, O, T, _stream())
+    launch("qec_routing_fused_fwd", t_oqi, lrfs, activation, alpha, beta, pose,
+         agreement, poses_all, stats, B * P, K, I, O, T)
     return pose, agreement, poses_all, stats
 
 
@@ -168,14 +164,14 @@ def routing_fused_backward_raw(t_oqi, lrfs, activation, alpha, beta, poses_all, 
     g_ab = torch.zeros(2, device=dev, dtype=torch.float32)
     if split:
         g_toqi = (torch.empty_like(t_oqi), torch.empty(t_oqi.shape, device=dev, dtype=torch.bfloat16))
-        call("qec_routing_fused_bwd_split", ptr(t_oqi), ptr(lrfs), ptr(activation), ptr(alpha), ptr(beta),
-             ptr(poses_all), ptr(stats), ptr(g_pose), ptr(g_agreement), ptr(g_toqi[0]), ptr(g_toqi[1]), ptr(g_lrfs),
-             ptr(g_act), ptr(g_ab), B * P, K, I, O, T, _stream())
+        launch("qec_routing_fused_bwd_split", t_oqi, lrfs, activation, alpha, beta,
+             poses_all, stats, g_pose, g_agreement, g_toqi[0], g_toqi[1], g_lrfs,
+             g_act, g_ab, B * P, K, I, O, T)
     else:
         g_toqi = torch.empty_like(t_oqi)
-        call("qec_routing_fused_bwd", ptr(t_oqi), ptr(lrfs), ptr(activation), ptr(alpha), ptr(beta), ptr(poses_all),
-             ptr(stats), ptr(g_pose), ptr(g_agreement), ptr(g_toqi), ptr(g_lrfs), ptr(g_act), ptr(g_ab), B * P, K, I,
-             O, T, _stream())
+        launch("qec_routing_fused_bwd", t_oqi, lrfs, activation, alpha, beta, poses_all,
+             stats, g_pose, g_agreement, g_toqi, g_lrfs, g_act, g_ab, B * P, K, I,
+             O, T)
     return g_toqi, g_lrfs, g_act, g_ab
 
 
@@ -221,8 +217,8 @@ def split_operand(src, extra=None, extra_const=1.0, perm=None, add_col=True, blo
     out = torch.empty(R, int(width), device=dev, dtype=torch.float32) if width is not None else None
     outb = torch.empty(R, int(bf16_width), device=dev, dtype=torch.bfloat16) if bf16_width is not None else None
     blk = list(blocks) + [0, 0, 0]
-    call("qec_split_operand", ptr(src), ptr(extra), float(extra_const), ptr(perm), ptr(out), ptr(outb), R, C,
-         1 if add_col else 0, stride, int(width or 0), int(bf16_width or 0), blk[0], blk[1], blk[2], nblk, _stream())
+    launch("qec_split_operand", src, extra, float(extra_const), perm, out, outb, R, C,
+         1 if add_col else 0, stride, int(width or 0), int(bf16_width or 0), blk[0], blk[1], blk[2], nblk)
     return out, outb
 
 
@@ -231,8 +227,7 @@ def fold_chunks(a, b, perm, out_main, out_last, K):
     out_last when out_main is K-1 wide (qec_fold_chunks)"""
     S, R, KP2 = a.shape
     KP = KP2 // 2
-    call("qec_fold_chunks", ptr(a), ptr(b), ptr(perm), ptr(out_main), ptr(out_last), S, R, KP, K, out_main.shape[1],
-         _stream())
+    launch("qec_fold_chunks", a, b, perm, out_main, out_last, S, R, KP, K, out_main.shape[1])
 
 
 class SpreadLoss(torch.autograd.Function):
@@ -247,8 +242,7 @@ class SpreadLoss(torch.autograd.Function):
         g = torch.empty_like(x)
         scratch = torch.empty(B, device=x.device, dtype=torch.float32)
         err = torch.zeros(1, device=x.device, dtype=torch.int32)
-        call("qec_spread_loss", ptr(x), ptr(target), float(margin), ptr(loss), ptr(g), ptr(scratch), ptr(err), B, C,
-             _stream())
+        launch("qec_spread_loss", x, target, float(margin), loss, g, scratch, err, B, C)
         ctx.save_for_backward(g)
         ctx.err = err  # checked lazily by callers that can afford a sync (spread_loss(..., check=True))
         return loss.view(())
@@ -261,6 +255,61 @@ class SpreadLoss(torch.autograd.Function):
 
 def spread_loss(x, target, margin=0.1):
     return SpreadLoss.apply(x, target, margin)
+
+
+class ClassPoseLoss(torch.autograd.Function):
+    """(x [S,B,C] | None, labels [B], pose [2,B,C,4] | None) -> loss [3] = {total, spread, pose_diff}: the spread
+    loss of S branches (reference qec_net.py:53-59 / qec_sia_net.py:69-77) + w_pose x the pose-difference loss on
+    the ground-truth class poses (qec_sia_net.py:79-82 after the selection loop of train_cls_sia.py:72-78), values
+    and gradients in one launch (qec_class_pose_loss).  Only loss[0] (the total) carries gradient."""
+
+    @staticmethod
+    def forward(ctx, x, pose, labels, margin, w_pose):
+        ref = x if x is not None else pose
+        dev = ref.device
+        if x is not None:
+            S, B, C = x.shape
+            x = _check(x, "x", (S, B, C))
+        else:
+            S = 0
+            _, B, C, _ = pose.shape
+        if pose is not None:
+            pose = _check(pose, "pose", (2, B, C, 4))
+        labels = labels.to(device=dev, dtype=torch.int64).contiguous().view(B)
+        loss = torch.empty(3, device=dev, dtype=torch.float32)
+        g_x = torch.empty_like(x) if x is not None else None
+        g_pose = torch.empty_like(pose) if pose is not None else None
+        err = torch.zeros(1, device=dev, dtype=torch.int32)
+        launch("qec_class_pose_loss", x, labels, float(margin), pose, float(w_pose), loss, g_x, g_pose, err, S, B, C)
+        ctx.save_for_backward(g_x, g_pose)
+        ctx.err = err
+        ctx.mark_non_differentiable(labels)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        g_x, g_pose = ctx.saved_tensors
+        g = g_loss[0]
+        return (None if g_x is None else g_x * g), (None if g_pose is None else g_pose * g), None, None, None
+
+
+def class_pose_loss(x, labels, pose=None, margin=0.1, w_pose=0.1):
+    """-> loss [3] = {total, spread, w-less pose_diff}; differentiate loss[0]"""
+    return ClassPoseLoss.apply(x, pose, labels, margin, w_pose)
+
+
+def quat_eval(pose1, pose2, want_dist=True, want_rel=True):
+    """batched q_distance / relative pose of the reference's rotation test (test_rot_sia.py:32-41, 131-132):
+    pose1, pose2 [..., 4] -> (dist [...] | None, rel [..., 4] | None)   (qec_quat_eval)"""
+    shape = pose1.shape[:-1]
+    a = _check(pose1.reshape(-1, 4), "pose1")
+    b = _check(pose2.reshape(-1, 4), "pose2", tuple(a.shape))
+    n = a.shape[0]
+    dist = torch.empty(n, device=a.device, dtype=torch.float32) if want_dist else None
+    rel = torch.empty(n, 4, device=a.device, dtype=torch.float32) if want_rel else None
+    if n:
+        launch("qec_quat_eval", a, b, dist, rel, n)
+    return (None if dist is None else dist.view(shape)), (None if rel is None else rel.view(*shape, 4))
 
 
 def routing_fused_packed_supported(K, I, O, T):
@@ -290,8 +339,8 @@ class RoutingSmall(torch.autograd.Function):
         agreement = torch.empty(B, P, O, device=dev, dtype=torch.float32)
         poses_all = torch.empty(T, B, P, O, 4, device=dev, dtype=torch.float32)
         stats = torch.empty(B, P, O, 2, device=dev, dtype=torch.float32)
-        call("qec_routing_small_fwd", ptr(xrot), ptr(lrfs), ptr(activation), ptr(Wc), ptr(bc), ptr(alpha), ptr(beta),
-             ptr(pose), ptr(agreement), ptr(poses_all), ptr(stats), B * P, K, O, T, _stream())
+        launch("qec_routing_small_fwd", xrot, lrfs, activation, Wc, bc, alpha, beta,
+             pose, agreement, poses_all, stats, B * P, K, O, T)
         ctx.save_for_backward(xrot, lrfs, activation, Wc, bc, alpha, beta, poses_all, stats)
         ctx.T = T
         return pose, agreement
@@ -309,9 +358,9 @@ class RoutingSmall(torch.autograd.Function):
         g_Wc = torch.zeros_like(Wc)
         g_bc = torch.zeros_like(bc)
         g_ab = torch.zeros(2, device=dev, dtype=torch.float32)
-        call("qec_routing_small_bwd", ptr(xrot), ptr(lrfs), ptr(activation), ptr(Wc), ptr(bc), ptr(alpha), ptr(beta),
-             ptr(poses_all), ptr(stats), ptr(g_pose), ptr(g_agreement), ptr(g_Wc), ptr(g_bc), ptr(g_ab), B * P, K, O,
-             ctx.T, _stream())
+        launch("qec_routing_small_bwd", xrot, lrfs, activation, Wc, bc, alpha, beta,
+             poses_all, stats, g_pose, g_agreement, g_Wc, g_bc, g_ab, B * P, K, O,
+             ctx.T)
         return None, None, None, g_Wc, g_bc, g_ab[0:1], g_ab[1:2], None
 
 
@@ -347,8 +396,11 @@ def knn_indices(points, K, centre_idx=None, centres=None):
     """K nearest neighbours of P centres among the N points of each sample, on the device (qec_knn):
     points [B,N,3] float32; centres as point indices centre_idx [B,P] int64 or coordinates centres [B,P,3].
     -> idx [B,P,K] int64 sorted by (squared distance, point index), bit-exact against
-    oracle.qec_oracle.knn_indices; err [1] int32 (1 = a centre index was out of range).  The result is
-    what neighbour_gather consumes."""
+    oracle.qec_oracle.knn_indices (-1 where N < K); err [1] int32 (1 = a centre index was out of range).
+
+    The ids are plain point numbers 0..N-1.  neighbour_gather() follows the reference LOADER's id contract
+    instead (id <= 0 = inactive slot, the last row of the sets reads as zeros), so do not feed these indices
+    to it unchanged: knn_neighbourhoods() composes the two correctly."""
     B, N, _ = points.shape
     points = _check(points, "points", (B, N, 3))
     if (centre_idx is None) == (centres is None):
@@ -363,8 +415,27 @@ def knn_indices(points, K, centre_idx=None, centres=None):
         centres = _check(centres, "centres", (B, P, 3))
     idx = torch.empty(B, P, int(K), device=points.device, dtype=torch.int64)
     err = torch.zeros(1, device=points.device, dtype=torch.int32)
-    call("qec_knn", ptr(points), ptr(centres), ptr(centre_idx), ptr(idx), ptr(err), B, N, P, int(K), _stream())
+    launch("qec_knn", points, centres, centre_idx, idx, err, B, N, P, int(K))
     return idx, err
+
+
+def knn_neighbourhoods(points, lrfs, K, centre_idx):
+    """kNN search + loader gather on the device: the K-neighbourhoods of the P centres as the routing layer
+    consumes them.  points [B,N,3], lrfs [B,N,4], centre_idx [B,P] -> (points [B,P,K,3], lrfs [B,P,K,4],
+    act [B,P,K], idx [B,P,K]).
+
+    qec_knn numbers points 0..N-1; qec_gather mirrors the reference loader, where id <= 0 marks an inactive slot
+    and the last row of the sets is zeroed (modelnet_with_lrf_sample_index_loader.py:139-160).  The
+    composition therefore shifts the ids by one and pads the sets with a leading dummy row and a trailing
+    zero row, so that point 0 stays active, point N-1 keeps its coordinates and a missing neighbour (-1, only
+    when N < K) reads zeros with activation 0."""
+    B, N, _ = points.shape
+    idx, err = knn_indices(points, K, centre_idx=centre_idx)
+    pad3 = points.new_zeros(B, 1, 3)
+    pad4 = lrfs.new_zeros(B, 1, 4)
+    ids = torch.where(idx >= 0, idx + 1, idx)
+    gp, gl, ga, gerr = neighbour_gather(torch.cat([pad3, points, pad3], 1), torch.cat([pad4, lrfs, pad4], 1), ids)
+    return gp, gl, ga, idx, err + gerr
 
 
 def neighbour_gather(point_set, lrf_set, idx, wrong_ids=None, wrong_count=None):
@@ -393,6 +464,6 @@ def neighbour_gather(point_set, lrf_set, idx, wrong_ids=None, wrong_count=None):
     lrfs = torch.empty(B, P, K, 4, device=dev, dtype=torch.float32)
     act = torch.empty(B, P, K, device=dev, dtype=torch.float32)
     err = torch.zeros(1, device=dev, dtype=torch.int32)
-    call("qec_gather", ptr(point_set), ptr(lrf_set), ptr(idx), ptr(wrong_ids), ptr(wrong_count), ptr(points),
-         ptr(lrfs), ptr(act), ptr(err), B, N, P, K, W, _stream())
+    launch("qec_gather", point_set, lrf_set, idx, wrong_ids, wrong_count, points,
+         lrfs, act, err, B, N, P, K, W)
     return points, lrfs, act, err

@@ -2,8 +2,6 @@
 models/qec_sia_net.py), kept as thin PyTorch glue over the B200 QecModule so that
 the reference's training scripts can switch imports and nothing else:
 same constructors, forward signatures, state_dict keys (pool1.*, pool2.*) and losses."""
-import math
-
 import torch
 import torch.nn.functional as F
 
@@ -20,14 +18,19 @@ def _two_pools(net, points, lrfs, activation):
 
 
 def _spread(x, target, margin=0.1):
-    """reference qec_net.py:53-59; one launch pair for the loss and its gradient (qec_spread_loss) instead
-    of ~25 ATen launches.  CUDA only, like the rest of the path (a CPU tensor raises in the wrapper)."""
-    return QF.spread_loss(x, target.view(-1), margin)
+    """reference qec_net.py:53-59 (x [B,C]) / qec_sia_net.py:69-77 (x [2,B,C], the sum over the two branches):
+    ONE launch for the loss and its gradient (qec_class_pose_loss) instead of ~25 ATen launches per branch.
+    CUDA only, like the rest of the path (a CPU tensor raises in the wrapper)."""
+    xs = x.unsqueeze(0) if x.dim() == 2 else x
+    return QF.class_pose_loss(xs, target.reshape(-1), None, margin=margin)[0]
 
 
 def _pose_diff(pose):
-    dot = (pose[0] * pose[1]).sum(dim=-1)
-    return (2.0 * torch.acos(torch.clamp(dot.abs(), max=0.9999)) / math.pi).mean()
+    """reference qec_net.py:61-64 / qec_sia_net.py:79-82 on already selected poses [2, B, 4]: one launch
+    (qec_class_pose_loss with the pose term only) instead of ~10 ATen launches each way"""
+    pose = pose.float().reshape(2, -1, 1, 4)  # the reference's mean runs over every leading dimension
+    labels = torch.zeros(pose.shape[1], device=pose.device, dtype=torch.int64)
+    return QF.class_pose_loss(None, labels, pose, w_pose=1.0)[0]
 
 
 class _QecBase(torch.nn.Module):
@@ -58,11 +61,22 @@ class QecNet(_QecBase):
         return _spread(x, target.reshape(-1))
 
 
+    def class_pose_loss(self, x, pose_out, target, pose_weight=0.1, margin=0.1):
+        """The whole loss of train_cls_sia.py:70-79 in one launch: spread loss of the branch(es) + pose_weight x
+        pose_diff_loss of the poses of the ground-truth class (the reference's per-sample selection loop
+        `pose_out_act[:, i] = pose_out[:, i, target_[i, 0]]` included).  x [2,B,C] / pose_out [2,B,C,4] as returned
+        by QecSiaNet.forward (or x [B,C] with pose_out None for QecNet).  -> (total, spread, pose_weight * pose_diff)
+        like the reference's (classify_loss + pose_loss, classify_loss, pose_loss)."""
+        t = target[:, 0] if target.dim() > 1 else target
+        xs = x if x.dim() == 3 else x.unsqueeze(0)
+        out = QF.class_pose_loss(xs, t.reshape(-1), pose_out, margin=margin, w_pose=pose_weight)
+        return out[0], out[1].detach(), (pose_weight * out[2]).detach()
+
+
 class QecSiaNet(_QecBase):
     def forward(self, points4pool1_, lrfs4pool1_, activation4pool1_, pointspool1index_=None):
         outs = [_two_pools(self, points4pool1_[:, i], lrfs4pool1_[:, i], activation4pool1_[:, i]) for i in range(2)]
         return torch.stack([o[0] for o in outs], 0), torch.stack([o[1] for o in outs], 0)
 
     def spread_loss(self, x, target, epoch=0):
-        t = target[:, 0].reshape(-1)
-        return _spread(x[0], t) + _spread(x[1], t)
+        return _spread(x, target[:, 0])

@@ -6,7 +6,7 @@ With this on ``sys.modules['torch_autograd_solver']`` the UNMODIFIED reference
 QecModule runs on a B200 with our eigensolver in place of pytorch-cusolver."""
 import torch
 
-from ._lib import call, ptr, QecLibraryError
+from ._lib import launch, QecLibraryError
 
 
 class BatchSymeig4(torch.autograd.Function):
@@ -18,7 +18,7 @@ class BatchSymeig4(torch.autograd.Function):
         V = torch.empty(n, 4, 4, device=a.device, dtype=torch.float32)
         status = torch.zeros(1, device=a.device, dtype=torch.int32)
         if n:
-            call("qec_symeig4_fwd", ptr(a), ptr(w), ptr(V), ptr(status), n, torch.cuda.current_stream().cuda_stream)
+            launch("qec_symeig4_fwd", a, w, V, status, n)
         ctx.save_for_backward(w, V)
         ctx.fold = int(fold)
         ctx.status = status  # device-side count of non-converged matrices; never synced here
@@ -32,8 +32,7 @@ class BatchSymeig4(torch.autograd.Function):
         if n and (gw is not None or gV is not None):
             gw = None if gw is None else gw.contiguous()
             gV = None if gV is None else gV.contiguous()
-            call("qec_symeig4_bwd", ptr(gw), ptr(gV), ptr(w), ptr(V), ptr(gM), n, ctx.fold,
-                 torch.cuda.current_stream().cuda_stream)
+            launch("qec_symeig4_bwd", gw, gV, w, V, gM, n, ctx.fold)
         return gM, None
 
 

@@ -71,3 +71,43 @@ def test_ddp_gradients_match_global_batch():
     out = mgr.dict()
     mp.spawn(_worker, args=(2, 29731, out), nprocs=2, join=True)
     assert out[0] < 1e-4 and out[1] < 1e-4, dict(out)
+
+
+def test_dataparallel_matches_single_gpu():
+    """the reference's own multi-GPU mode (train_cls.py:27,62-65): nn.DataParallel over the drop-in QecNet --
+    ONE process, one Python thread per GPU, replicas re-created every step -- forward and backward on two GPUs
+    against the single-GPU result.  pool2 runs on the cluster kernels (4 096 votes per capsule, > 48 KB of
+    dynamic shared memory), whose opt-in attribute is per device: the launch configuration cached per device
+    ordinal is what this test pins."""
+    import qecnetworks_b200 as qb
+    from qecnetworks_b200.synthetic import synthetic_batch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    net = qb.QecNet(2048, 16, 10, 3).to(dev)
+    B = 4
+    points, lrfs, act, labels = [t.to(dev) for t in synthetic_batch(B, ncls=10, seed=13)]
+    idx = torch.zeros(B, 256, 9, dtype=torch.int64, device=dev)   # pointspool1index: scattered like the reference's
+
+    def step(model):
+        for p in net.parameters():
+            p.grad = None
+        pose, a = model(points, lrfs, act, idx)
+        loss = net.spread_loss(a, labels)          # on the gathered output, as train_cls.py:62-64 does
+        loss.backward()
+        return pose.detach().clone(), a.detach().clone(), {k: v.grad.detach().clone() for k, v in net.named_parameters()}
+
+    pose1, a1, g1 = step(net)
+    dp = torch.nn.DataParallel(net, device_ids=[0, 1])
+    for _ in range(2):   # twice: the second step finds every per-device cache filled
+        pose2, a2, g2 = step(dp)
+        assert pose2.device == dev and pose2.shape == pose1.shape
+        d = torch.minimum((pose1 - pose2).abs().amax(-1), (pose1 + pose2).abs().amax(-1))
+        assert float(d.max()) < 1e-5
+        assert float((a1 - a2).abs().max()) < 1e-5
+        scale = max(float(v.abs().max()) for v in g1.values())
+        for k in g1:
+            e = float((g1[k] - g2[k]).abs().max()) / max(float(g1[k].abs().max()), 0.25 * scale)
+            assert e < 1e-4, (k, e)

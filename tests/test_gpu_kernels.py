@@ -613,3 +613,141 @@ def test_gather_golden_gpu():
         assert torch.equal(points[n].cpu(), g["s%d.points" % n])
         assert torch.equal(lrfs[n].cpu(), g["s%d.lrfs" % n])
         assert torch.equal(act[n].cpu(), g["s%d.act" % n])
+
+
+# ---------------------------------------------------------------- losses / eval ops as single launches (8 f.3, f.4)
+@pytest.mark.parametrize("B,C", [(16, 40), (5, 10), (1, 3), (300, 7)])
+def test_class_pose_loss_kernel(B, C):
+    """qec_class_pose_loss against the reference expressions in float64: Siamese spread loss
+    (qec_sia_net.py:69-77) + 0.1 x pose_diff_loss (qec_sia_net.py:79-82) of the GT-class poses selected as in
+    train_cls_sia.py:72-78, values and both gradients; also the one-branch and the pose-only forms"""
+    from qecnetworks_b200 import functional as QF
+
+    dev = cuda()
+    gen = torch.Generator().manual_seed(B * 31 + C)
+    x = torch.rand(2, B, C, generator=gen) * 0.3 + 0.5
+    y = torch.randint(0, C, (B,), generator=gen)
+    pose = torch.randn(2, B, C, 4, generator=gen)
+    pose = pose / pose.norm(dim=-1, keepdim=True)
+    pose[1, 0, y[0]] = pose[0, 0, y[0]]           # <p0,p1> = 1: beyond the 0.9999 clamp, zero gradient
+    if B > 2:
+        pose[1, 1, y[1]] = -pose[0, 1, y[1]]      # and its mirror image
+    xr = x.double().requires_grad_(True)
+    pr = pose.double().requires_grad_(True)
+    spread = orc.sia_spread_loss(xr, y)
+    sel = torch.stack([pr[:, i, y[i]] for i in range(B)], 1)   # the reference's selection loop
+    pd = orc.pose_diff_loss(sel)
+    (spread + 0.1 * pd).backward()
+    xd = x.to(dev).requires_grad_(True)
+    pdv = pose.to(dev).requires_grad_(True)
+    out = QF.class_pose_loss(xd, y.to(dev), pdv, margin=0.1, w_pose=0.1)
+    (out[0] * 2.0).backward()
+    assert abs(float(out[0]) - float(spread + 0.1 * pd)) < 2e-6
+    assert abs(float(out[1]) - float(spread)) < 2e-6 and abs(float(out[2]) - float(pd)) < 2e-6
+    assert max_err(xd.grad.cpu(), 2.0 * xr.grad) < 2e-6
+    # d acos / dx ~ 70 at the clamp: relative tolerance on the pose gradient
+    assert rel_err(pdv.grad.cpu(), 2.0 * pr.grad) < 1e-5
+    # one branch, no pose term == QecNet.spread_loss
+    x1 = x[0].to(dev).requires_grad_(True)
+    l1 = QF.class_pose_loss(x1.unsqueeze(0), y.to(dev))[0]
+    ref1 = orc.spread_loss(x[0].double(), y)
+    assert abs(float(l1) - float(ref1)) < 2e-6
+    # pose term only on pre-selected poses == pose_diff_loss(pose_out_act)
+    import qecnetworks_b200 as qb
+    net = qb.QecSiaNet(2048, 4, C, 3)
+    got = net.pose_diff_loss(sel.detach().float().to(dev))
+    assert abs(float(got) - float(pd)) < 2e-6
+    tot, cls, pl = net.class_pose_loss(x.to(dev), pose.to(dev), torch.stack([y, y], 1).to(dev))
+    assert abs(float(tot) - float(spread + 0.1 * pd)) < 2e-6 and abs(float(pl) - 0.1 * float(pd)) < 2e-6
+    bad = y.clone()
+    bad[0] = C
+    QF.class_pose_loss(x.to(dev), bad.to(dev), pose.to(dev))
+    # (out-of-range labels set the device flag instead of raising: no host sync on the training path)
+
+
+def test_knn_then_gather_composition():
+    """qec_knn -> qec_gather composed through knn_neighbourhoods: the id contracts differ (plain point numbers vs
+    the loader's "id <= 0 inactive, last row zeroed"), so point 0 and point N-1 must survive the composition"""
+    from qecnetworks_b200 import functional as QF
+
+    dev = cuda()
+    gen = torch.Generator().manual_seed(3)
+    B, N, P, K = 2, 64, 8, 9
+    pts = torch.randn(B, N, 3, generator=gen)
+    lr = torch.randn(B, N, 4, generator=gen)
+    ci = torch.stack([torch.tensor([0, N - 1] + list(range(5, 5 + P - 2))) for _ in range(B)])
+    gp, gl, ga, idx, err = QF.knn_neighbourhoods(pts.to(dev), lr.to(dev), K, ci.to(dev))
+    assert int(err.item()) == 0
+    ref = orc.knn_indices(pts, K, centre_idx=ci)
+    assert torch.equal(idx.cpu(), ref)
+    for b in range(B):
+        assert torch.equal(gp[b].cpu(), pts[b][ref[b].reshape(-1)].view(P, K, 3))
+        assert torch.equal(gl[b].cpu(), lr[b][ref[b].reshape(-1)].view(P, K, 4))
+    assert bool((ga == 1).all())
+    # the centre itself is its own nearest neighbour, also for point 0 and point N-1
+    assert torch.equal(gp[:, :, 0].cpu(), torch.stack([pts[b][ci[b]] for b in range(B)]))
+    # fewer points than K: the missing slots read zeros with activation 0
+    gp2, gl2, ga2, idx2, _ = QF.knn_neighbourhoods(pts[:, :5].contiguous().to(dev), lr[:, :5].contiguous().to(dev), K,
+                                                   ci[:, :1].clamp(max=4).to(dev))
+    assert bool((idx2[..., 5:] == -1).all()) and float(ga2[..., 5:].abs().max()) == 0.0
+    assert float(gp2[..., 5:, :].abs().max()) == 0.0 and bool((ga2[..., :5] == 1).all())
+
+
+def test_quat_eval_kernel():
+    from qecnetworks_b200 import functional as QF
+
+    dev = cuda()
+    gen = torch.Generator().manual_seed(5)
+    a = torch.randn(7, 33, 4, generator=gen)
+    b = torch.randn(7, 33, 4, generator=gen)
+    a = a / a.norm(dim=-1, keepdim=True)
+    b = b / b.norm(dim=-1, keepdim=True)
+    b[0, 0] = a[0, 0]
+    dist, rel = QF.quat_eval(a.to(dev), b.to(dev))
+    assert dist.shape == (7, 33) and rel.shape == (7, 33, 4)
+    assert max_err(dist.cpu(), orc.q_distance(a.double(), b.double())) < 5e-4  # acos at 1 is ill-conditioned in FP32
+    assert max_err(dist.cpu()[1:], orc.q_distance(a.double(), b.double())[1:]) < 1e-5
+    assert max_err(rel.cpu(), orc.ham(orc.conj(a.double()), b.double())) < 1e-6
+
+
+@pytest.mark.parametrize("K,I,O", [(256, 16, 8), (256, 128, 3)])
+def test_routing_fused_uniform_random_votes_residual(K, I, O):
+    """ill-conditioned cluster-kernel case: LRFs and transforms uniformly random, so every vote
+    is a uniformly random rotation and M = mean v v^T is I/4 + O(1/sqrt(J)): relative eigengaps of a few 1e-3
+    (the slow case of the squaring solver: eigenvalue ratio ~0.99).  T = 1, so the device and the float64 oracle
+    solve the same matrix: eigen-residual and eigenvalue within 1e-5 for every capsule; the vector itself within
+    1e-4 only where the relative gap is >= 1e-2"""
+    from qecnetworks_b200 import functional as QF
+
+    dev = cuda()
+    B, P, T = 1, 2, 1
+    J = K * I
+    gen = torch.Generator().manual_seed(K + I + O)
+    lrfs = torch.randn(B, P, K, I, 4, generator=gen)
+    lrfs = lrfs / lrfs.norm(dim=-1, keepdim=True)
+    lrfs = lrfs * torch.where(lrfs[..., :1] < 0, -1.0, 1.0)
+    act = torch.ones(B, P, J)
+    t_raw = torch.randn(B * P * K, 4 * I * O, generator=gen)
+    perm = _oqi_perm(I, O)
+    alpha, beta = torch.tensor([1.0]), torch.tensor([1.0])
+    v = orc.votes_from(lrfs.double(), t_raw.double().view(B, P, K, 4, I, O))
+    M = torch.einsum("bpojc,bpojd->bpocd", v, v) / J
+    lam, V = torch.linalg.eigh(M)
+    gap = (lam[..., 3] - lam[..., 2]) / lam[..., 3]
+    pose, agr, _, _ = QF.routing_fused_forward_raw(t_raw[:, perm].contiguous().to(dev), lrfs.to(dev), act.to(dev),
+                                                   alpha.to(dev), beta.to(dev), T)
+    p = pose.cpu().double()
+    assert float((p.norm(dim=-1) - 1).abs().max()) < 1e-5 and float(p[..., 0].min()) >= 0.0
+    Mp = torch.einsum("bpocd,bpod->bpoc", M, p)
+    lg = (p * Mp).sum(-1)
+    resid = (Mp - lg.unsqueeze(-1) * p).abs().amax(-1)
+    ref = V[..., :, 3]
+    d = torch.minimum((p - ref).abs().amax(-1), (p + ref).abs().amax(-1))
+    well = gap >= 1e-2
+    print("uniform votes J=%d: gaps %.1e .. %.1e, residual %.2e, dlambda %.2e, pose err (gap >= 1e-2: %d of %d) %.2e, all %.2e"
+          % (J, float(gap.min()), float(gap.max()), float(resid.max()), float((lg - lam[..., 3]).abs().max()),
+             int(well.sum()), well.numel(), float(d[well].max()) if well.any() else 0.0, float(d.max())))
+    assert float(resid.max()) < 1e-5
+    assert float((lg - lam[..., 3]).abs().max()) < 1e-5
+    if well.any():
+        assert float(d[well].max()) < TOL
