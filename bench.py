@@ -10,6 +10,13 @@ ModelNet40-shaped batch (BASELINE.json configs[1]: B=32 per GPU, 256 patches x 9
 data-parallel gradient all-reduce (N > 1) and the Adam update.  Weak scaling: the
 per-GPU batch is fixed, `value` is the whole-job samples/s (max over ranks of the
 CUDA-event time).  Prints ONE JSON line on rank 0.
+
+The other BASELINE.json configs are parity-test cases first; `--config` measures them too, each as one JSON
+line with the same keys (run by hand, results under profiles/):
+    --config 1   configs[0]: single QecModule layer forward, B=8, 64 x 9-NN, O=128, T=3 (latency, CUDA graph)
+    --config 2   configs[1] (default; configs[2] is the same under torchrun)
+    --config 4   configs[3]: Siamese QecSiaNet train step, B=16 pairs (train_cls_sia.py shape)
+    --config 5   configs[4]: routing stress sweep, B=1024 inference, corners K x O x T
 """
 import argparse
 import json
@@ -30,16 +37,24 @@ UNIT = "samples/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 4, 5], help="BASELINE.json config (1-based)")
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 100; 5 for --impl reference)")
+    ap.add_argument("--min-timed-s", type=float, default=0.0,
+                    help="raise --steps until the timed region lasts at least this long (0 = exactly --steps)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="samples per GPU (weak scaling)")
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU (weak scaling); default per config")
     ap.add_argument("--channels", type=int, default=128)
     ap.add_argument("--classes", type=int, default=40)
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.batch is None:
+        a.batch = {1: 8, 2: 32, 4: 16, 5: 1024}[a.config]
+    if a.steps is None:
+        a.steps = 100 if a.impl == "b200" else 5
+    return a
 
 
 def workload_name(a):
@@ -70,11 +85,35 @@ def cpu_train_step_factory(a, batch):
     return step
 
 
+def cpu_baseline_config2(a):
+    """cpu_baseline of the default run: one train step of the oracle port at B = 2, 4 and 8 (one warm-up first) --
+    about 10-20 s of CPU work.  The per-sample cost of the CPU path is flat in B (it is a sequence of ATen ops
+    over per-vote tensors; SURVEY.md App. C.2 measured 0.88 / 0.81 samples/s at B = 4 / 8), which `flatness`
+    shows for this box, so the B = 8 figure stands for the stated B = 32 (which would need ~32 GB and ~40 s per
+    step)."""
+    flat = {}
+    cpu_train_step_factory(a, 2)()
+    for b in (2, 4, 8):
+        step = cpu_train_step_factory(a, b)
+        t0 = time.perf_counter()
+        step()
+        flat[str(b)] = b / (time.perf_counter() - t0)
+    return {"value": flat["8"], "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+            "flatness_samples_per_s_by_B": flat,
+            "sample": "oracle port of the reference CPU path (torch eigh in place of cuSOLVER, 1e-6 noise on): one "
+                      "train step of the same net at B=8 after a warm-up; samples/s is flat in B (see "
+                      "flatness_samples_per_s_by_B), the stated B=32 would need ~32 GB of host memory"}
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_b = 2
+    if a.config != 2:
+        print(json.dumps({"impl": "reference", "unavailable": "the reference arm times BASELINE configs[1] only; the "
+                          "other configs carry their CPU figure in cpu_baseline"}))
+        return
+    sample_b = 8
     step = cpu_train_step_factory(a, sample_b)
     for _ in range(a.warmup):
         step()
@@ -84,7 +123,8 @@ def run_reference(a):
     dt = (time.perf_counter() - t0) / max(a.steps, 1)
     value = sample_b / dt
     cores = os.cpu_count() or 1
-    sample = "oracle port of the reference CPU path (torch eigh), B=%d per step, same net/config, noise on" % sample_b
+    sample = ("oracle port of the reference CPU path (torch eigh), each step = one train step on a bounded sample of "
+              "B=%d of the B=%d batch, same net/config, noise on; samples/s of the CPU path is flat in B" % (sample_b, a.batch))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -209,41 +249,96 @@ class ClockSampler:
 
 # ------------------------------------------------------------------ roofline accounting
 def kernel_work(name, dims, T):
-    """Algorithmic bytes / FLOP per launch.
+    """-> (bytes, FLOP, impl_bytes) per launch.  `bytes` / FLOP are the nominal ALGORITHMIC figures of SURVEY.md 8(d)
+    / BASELINE.md section 4 (what `roofline.achieved` and `frac` are computed from): a routing forward moves
+    16 Nv + 4 Nn + 20 Nc bytes, a routing backward 32 Nv + 4 Nn + 20 Nc.  `impl_bytes` is what this
+    implementation's data formats move per launch (e.g. the pre-split transform gradient: +8 B per vote; LRFs read
+    as well as activations); the excess over `bytes` is overhead traffic, not useful work.
     Nv votes, Nc output capsules, Nn input LRFs."""
     if name in ("qec_routing_fwd", "qec_routing_bwd"):
         BP, O, J, T = dims[:4]
         Nv, Nc, Nn = BP * O * J, BP * O, BP * J
         if name == "qec_routing_fwd":
-            return 16 * Nv + 4 * Nn + 20 * Nc, 49 * T * Nv + 2000 * T * Nc + 20 * Nc
-        return 32 * Nv + 4 * Nn + 20 * Nc, 2 * 49 * T * Nv + 300 * T * Nc
+            by = 16 * Nv + 4 * Nn + 20 * Nc
+            return by, 49 * T * Nv + 2000 * T * Nc + 20 * Nc, by
+        by = 32 * Nv + 4 * Nn + 20 * Nc
+        return by, 2 * 49 * T * Nv + 300 * T * Nc, by
     if name in ("qec_votes_fwd", "qec_votes_bwd"):
         BP, K, I, O = dims[:4]
         Nv, Nn = BP * K * I * O, BP * K * I
         if name == "qec_votes_fwd":
-            return 32 * Nv + 16 * Nn, 48 * Nv
-        return 48 * Nv + 32 * Nn, 2 * 48 * Nv
+            return 32 * Nv + 16 * Nn, 48 * Nv, 32 * Nv + 16 * Nn
+        return 48 * Nv + 32 * Nn, 2 * 48 * Nv, 48 * Nv + 32 * Nn
     if name in ("qec_routing_fused_fwd", "qec_routing_fused_bwd", "qec_routing_fused_bwd_split"):
         # votes generated on chip from the transforms: t read once (fwd) + its gradient written once (bwd)
         BP, K, I, O, T = dims[:5]
         Nv, Nc, Nn = BP * K * I * O, BP * O, BP * K * I
         if name == "qec_routing_fused_fwd":
-            return 16 * Nv + 20 * Nn + 20 * Nc, (48 + 49 * T) * Nv + 2000 * T * Nc + 20 * Nc
+            return 16 * Nv + 4 * Nn + 20 * Nc, (48 + 49 * T) * Nv + 2000 * T * Nc + 20 * Nc, 16 * Nv + 20 * Nn + 20 * Nc
         # _split writes the transform gradient as TF32 hi (4 B) + BF16 remainder (2 B) for the tensor-core GEMMs
         extra = 8 * Nv if name.endswith("_split") else 0
-        return 32 * Nv + extra + 40 * Nn + 20 * Nc, (2 * 48 + 2 * 49 * T) * Nv + 300 * T * Nc
+        return (32 * Nv + 4 * Nn + 20 * Nc, (2 * 48 + 2 * 49 * T) * Nv + 300 * T * Nc,
+                32 * Nv + extra + 40 * Nn + 20 * Nc)
     if name in ("qec_routing_small_fwd", "qec_routing_small_bwd"):
-        # I = 1, composed transform (24 FLOP / vote) evaluated in-kernel: no transform tensor at all
+        # I = 1, composed transform (24 FLOP / vote) evaluated in-kernel: no transform or vote tensor at all
         BP, K, O, T = dims[:4]
         Nv, Nc, Nn = BP * K * O, BP * O, BP * K
         if name == "qec_routing_small_fwd":
-            return 32 * Nn + 20 * Nc, (24 + 48 + 49 * T) * Nv + 2000 * T * Nc + 20 * Nc
-        return 32 * Nn + (16 * T + 28) * Nc, (2 * (24 + 48) + 49 * (T + 1)) * Nv + 300 * Nc
+            return (16 * Nv + 4 * Nn + 20 * Nc, (24 + 48 + 49 * T) * Nv + 2000 * T * Nc + 20 * Nc,
+                    32 * Nn + (16 * T + 28) * Nc)
+        return (32 * Nv + 4 * Nn + 20 * Nc, (2 * (24 + 48) + 49 * (T + 1)) * Nv + 300 * Nc,
+                32 * Nn + (16 * T + 28) * Nc)
     if name in ("qec_lrf_mean_fwd", "qec_lrf_mean_bwd"):
         BP, K, I = dims[:3]
         Nn, Nm = BP * K * I, BP * I
-        return (16 + 4 + 12 + 12) * Nn + 16 * Nm, 40 * Nn + 2000 * Nm
-    return 0, 0
+        by = (16 + 4 + 12 + 12) * Nn + 16 * Nm
+        return by, 40 * Nn + 2000 * Nm, by
+    return 0, 0, 0
+
+
+def roofline_of(k, hbm_peak, peak_src, fp32_peak):
+    """roofline object of one timed kernel record: the roof that gives the LONGER time for the section-8(d) work names
+    the bound and `frac`; when the two roofs are within 20 % of each other both fractions are given"""
+    hbm_time = k["alg_bytes"] / (hbm_peak * 1e9)
+    fp_time = k["alg_flop"] / (fp32_peak * 1e12) if fp32_peak else 0.0
+    traffic = load_traffic(k["kernel"])
+    r = {"kernel": k["kernel"], "dims": k["dims"], "ms": k["ms"], "traffic": traffic,
+         "alg_bytes": k["alg_bytes"], "alg_bytes_impl": k["impl_bytes"], "alg_flop": k["alg_flop"],
+         "traffic_over_alg": (traffic / k["alg_bytes"]) if traffic and k["alg_bytes"] else None,
+         "accounting": "SURVEY.md 8(d) nominal bytes / FLOP; alg_bytes_impl = bytes of this implementation's formats"}
+    if hbm_time >= fp_time:
+        r.update({"bound": "hbm", "achieved": k["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": k["hbm_frac"],
+                  "peak_source": peak_src})
+    else:
+        r.update({"bound": "fp32", "achieved": k["fp32_tflops"], "peak": fp32_peak, "unit": "TFLOP/s",
+                  "frac": k["fp32_frac"], "peak_source": "FFMA microbenchmark in this run (qec_ffma_peak)",
+                  "note": "FP32-FMA-bound by design (4x4 quaternion algebra is not a dense contraction); "
+                          "schema extension of hbm|tensor"})
+    if max(hbm_time, fp_time) > 0 and min(hbm_time, fp_time) >= 0.8 * max(hbm_time, fp_time):
+        r["frac_hbm"], r["frac_fp32"] = k["hbm_frac"], k["fp32_frac"]
+    else:
+        r["other_roof_frac"] = k["fp32_frac"] if r["bound"] == "hbm" else k["hbm_frac"]
+    return r
+
+
+def kernel_records(rec, nprof, T, hbm_peak, fp32_peak, step_ms):
+    kernels = []
+    for (name, dims), times in rec.items():
+        per = sum(times) / len(times)
+        calls = len(times) / nprof
+        by, fl, impl = kernel_work(name, dims, T)
+        kernels.append({
+            "kernel": name, "dims": list(dims), "calls_per_step": calls, "ms": per, "ms_per_step": per * calls,
+            "alg_bytes": by, "impl_bytes": impl, "alg_flop": fl,
+            "hbm_gbs": by / (per * 1e-3) / 1e9 if per > 0 else None,
+            "hbm_frac": by / (per * 1e-3) / 1e9 / hbm_peak if per > 0 else None,
+            "fp32_tflops": fl / (per * 1e-3) / 1e12 if per > 0 else None,
+            "fp32_frac": fl / (per * 1e-3) / 1e12 / fp32_peak if per > 0 and fp32_peak else None,
+        })
+    kernels.sort(key=lambda k: -k["ms_per_step"])
+    for k in kernels:
+        k["share_of_step"] = k["ms_per_step"] / step_ms if step_ms > 0 else None
+    return kernels
 
 
 def measure_fp32_peak(torch, _lib, dev):
@@ -402,6 +497,17 @@ def run_b200(a):
     sampler.start()          # NVML initialisation happens here, outside the timed region ...
     run_step(devb[0])        # ... and one more untimed step puts every rank back into steady state
     barrier()
+    if a.min_timed_s > 0:  # the builder's own runs: make the timed region long enough to be stable
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for i in range(3):
+            run_step(devb[i % NB])
+        p1.record()
+        barrier()
+        est = torch.tensor([p0.elapsed_time(p1) / 3.0], device=dev)
+        if world > 1:
+            dist.all_reduce(est, op=dist.ReduceOp.MAX)  # every rank must run the same number of steps
+        a.steps = max(a.steps, int(a.min_timed_s * 1e3 / max(float(est.item()), 1e-3)) + 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(a.steps):
@@ -467,6 +573,7 @@ def run_b200(a):
     kernels = []
     roofline = None
     fp32_peak = None
+    extra = {}
     if True:  # every rank runs the pass (the step contains the gradient all-reduce); rank 0 reports
         fp32_peak = measure_fp32_peak(torch, _lib, dev)
         hbm_peak, peak_src = load_peaks()
@@ -478,55 +585,17 @@ def run_b200(a):
             train_step(*static)
         torch.cuda.synchronize()
         rec = _lib.stop_kernel_timing()
-        tot = 0.0
-        for (name, dims), times in rec.items():
-            per = sum(times) / len(times)
-            calls = len(times) / nprof
-            by, fl = kernel_work(name, dims, a.iters)
-            kernels.append({
-                "kernel": name, "dims": list(dims), "calls_per_step": calls, "ms": per, "ms_per_step": per * calls,
-                "alg_bytes": by, "alg_flop": fl,
-                "hbm_gbs": by / (per * 1e-3) / 1e9 if per > 0 else None,
-                "hbm_frac": by / (per * 1e-3) / 1e9 / hbm_peak if per > 0 else None,
-                "fp32_tflops": fl / (per * 1e-3) / 1e12 if per > 0 else None,
-                "fp32_frac": fl / (per * 1e-3) / 1e12 / fp32_peak if per > 0 and fp32_peak else None,
-            })
-            tot += per * calls
-        kernels.sort(key=lambda k: -k["ms_per_step"])
-        for k in kernels:
-            k["share_of_step"] = k["ms_per_step"] / ms if ms > 0 else None
+        kernels = kernel_records(rec, nprof, a.iters, hbm_peak, fp32_peak, ms)
         if kernels:
-            top = kernels[0]
-            hbm_time = top["alg_bytes"] / (hbm_peak * 1e9)
-            fp_time = top["alg_flop"] / (fp32_peak * 1e12)
-            if hbm_time >= fp_time:
-                roofline = {"kernel": top["kernel"], "dims": top["dims"], "bound": "hbm", "achieved": top["hbm_gbs"],
-                            "peak": hbm_peak, "unit": "GB/s", "frac": top["hbm_frac"], "traffic": load_traffic(top["kernel"]),
-                            "peak_source": peak_src, "ms": top["ms"]}
-            else:
-                roofline = {"kernel": top["kernel"], "dims": top["dims"], "bound": "fp32", "achieved": top["fp32_tflops"],
-                            "peak": fp32_peak, "unit": "TFLOP/s", "frac": top["fp32_frac"],
-                            "traffic": load_traffic(top["kernel"]), "alg_bytes": top["alg_bytes"],
-                            "hbm_frac": top["hbm_frac"],
-                            "peak_source": "FFMA microbenchmark in this run (qec_ffma_peak)", "ms": top["ms"],
-                            "note": "FP32-FMA-bound by design (4x4 quaternion algebra is not a dense contraction); "
-                                    "schema extension of hbm|tensor"}
-            roofline["own_kernels_ms_per_step"] = tot
+            roofline = roofline_of(kernels[0], hbm_peak, peak_src, fp32_peak)
+            roofline["own_kernels_ms_per_step"] = sum(k["ms_per_step"] for k in kernels)
+            if len(kernels) > 1:  # the second-largest kernel (the forward twin of the dominant one)
+                extra["roofline_second"] = roofline_of(kernels[1], hbm_peak, peak_src, fp32_peak)
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ----------------------
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        sample_b = 4
-        cstep = cpu_train_step_factory(a, sample_b)
-        cstep()
-        best = float("inf")
-        for _ in range(2):
-            t0 = time.perf_counter()
-            cstep()
-            best = min(best, time.perf_counter() - t0)
-        cpu = {"value": sample_b / best, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": "oracle port of the reference CPU path (torch eigh in place of cuSOLVER, 1e-6 noise on), "
-                         "one train step at B=%d, best of 2 after 1 warm-up" % sample_b}
+        cpu = cpu_baseline_config2(a)
 
     if rank == 0:
         gb = a.batch * world
@@ -555,6 +624,7 @@ def run_b200(a):
             "kernels": kernels,
             "final_loss": last,
         }
+        out.update(extra)
         print(json.dumps(out), flush=True)
     if world > 1:
         # Tear-down of a process group whose communicator is still referenced by a captured CUDA
@@ -567,6 +637,360 @@ def run_b200(a):
         os._exit(0)
 
 
+# ------------------------------------------------------------------ the other BASELINE configs (one GPU)
+def _time_graph(torch, fn, n):
+    """n calls of fn between two events on the current stream -> ms per call"""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(n):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def _capture(torch, body, warm=3):
+    """run `body` a few times on a side stream, then capture it; -> (graph | None, result of the captured call)"""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(warm):
+            out = body()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = body()
+        return g, out
+    except Exception as e:
+        sys.stderr.write("CUDA graph capture failed (%s); running eagerly\n" % (e,))
+        torch.cuda.synchronize()
+        return None, out
+
+
+def run_other_config(a):
+    import torch
+
+    import qecnetworks_b200 as qb
+    from qecnetworks_b200 import _lib, ddp
+    from qecnetworks_b200.synthetic import synthetic_batch, siamese_pair
+    from oracle import qec_oracle as orc  # cpu_baseline leg only (the CPU arm; never on the measured path)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the QEC kernels have no CPU fallback")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"unavailable": "--config %d is a single-GPU measurement" % a.config}))
+        return
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(0)
+    hbm_peak, peak_src = load_peaks()
+    fp32_peak = measure_fp32_peak(torch, _lib, dev)
+    W = max(a.warmup, 3)
+    NB = 4
+    sampler = ClockSampler(0)
+    extra = {}
+    cpu = None
+
+    def pinned(ts):
+        return tuple(t.pin_memory() for t in ts)
+
+    def kernel_pass(step, nprof=3):
+        _lib.start_kernel_timing()
+        for _ in range(nprof):
+            step()
+        torch.cuda.synchronize()
+        return _lib.stop_kernel_timing()
+
+    if a.config == 1:
+        # ---- configs[0]: ONE routing layer, forward only (inference), B=8, 64 centres x 9-NN, O=128, T=3
+        B, P, K, O, T = a.batch, 64, 9, a.channels, a.iters
+        mod = qb.QecModule(1, O, num_iterations=T, num_neighbours=K, num_patches=P).to(dev)
+        host = []
+        for i in range(NB):
+            pts, lr, ac, _ = synthetic_batch(B, P=P, K=K, seed=1234 + i)
+            host.append(pinned((pts, lr.unsqueeze(-2).contiguous(), ac.unsqueeze(-1).contiguous())))
+        devb = [tuple(t.to(dev) for t in hb) for hb in host]
+        static = tuple(torch.empty_like(t) for t in devb[0])
+
+        def body():
+            with torch.no_grad():
+                return mod(*static)
+
+        graph, out = _capture(torch, body)
+        l0 = qb.kernel_launches()
+        body()
+        launches = qb.kernel_launches() - l0
+
+        def dev_step(i):
+            for s_, t_ in zip(static, devb[i % NB]):
+                s_.copy_(t_, non_blocking=True)
+            graph.replay() if graph is not None else body()
+
+        res_host = pinned((torch.empty(out[0].shape), torch.empty(out[1].shape)))
+
+        def e2e_step(i):
+            for s_, t_ in zip(static, host[i % NB]):
+                s_.copy_(t_, non_blocking=True)
+            o = out if graph is not None else None
+            if graph is not None:
+                graph.replay()
+            else:
+                o = body()
+            res_host[0].copy_(o[0], non_blocking=True)
+            res_host[1].copy_(o[1], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        # the layer alone, no input copy: the latency the roofline (6.5 us) is about
+        def bare_step(i):
+            graph.replay() if graph is not None else body()
+
+        sampler.start()
+        _time_graph(torch, dev_step, W)
+        if a.min_timed_s > 0:
+            est = _time_graph(torch, dev_step, 20)
+            a.steps = max(a.steps, int(a.min_timed_s * 1e3 / max(est, 1e-4)) + 1)
+        ms = _time_graph(torch, dev_step, a.steps)
+        ms_bare = _time_graph(torch, bare_step, a.steps)
+        ms_e2e = _time_graph(torch, e2e_step, a.steps)
+        clocks = sampler.stop()
+        rec = kernel_pass(body)
+        kernels = kernel_records(rec, 3, T, hbm_peak, fp32_peak, ms)
+        units = B
+        workload = ("configs[0]: single QecModule routing layer forward (inference), B=%d, %d LRF centres x %d-NN, "
+                    "in_channels=1, out_channels=%d, T=%d, synthetic clustered LRFs" % (B, P, K, O, T))
+        h2d = sum(t.numel() * t.element_size() for t in host[0])
+        d2h = sum(t.numel() * 4 for t in res_host)
+        extra["latency_us"] = {"layer_graph_replay": ms_bare * 1e3, "with_device_input_copy": ms * 1e3,
+                               "end_to_end_from_host": ms_e2e * 1e3,
+                               "roofline_us": max(kernel_work("qec_routing_small_fwd", (B * P, K, O, T), T)[1] / (fp32_peak * 1e12),
+                                                  kernel_work("qec_routing_small_fwd", (B * P, K, O, T), T)[0] / (hbm_peak * 1e9)) * 1e6}
+        if not a.no_cpu_baseline:
+            p = orc.init_module_params(1, O, seed=0)
+            pts, lr, ac = [t for t in host[0]]
+            torch.set_num_threads(os.cpu_count() or 1)
+            best = float("inf")
+            for r in range(4):
+                t0 = time.perf_counter()
+                with torch.no_grad():
+                    orc.qec_module_forward(p, pts, lr, ac, T, noise=1e-6)
+                if r:
+                    best = min(best, time.perf_counter() - t0)
+            cpu = {"value": B / best, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": "oracle port of the reference CPU path: the same layer forward at the same B=%d under no_grad, "
+                             "best of 3 after a warm-up (%.1f ms)" % (B, best * 1e3)}
+        final = float(out[1].float().mean())
+        cfg_extra = {"layer": "QecModule(1, %d, T=%d, K=%d, P=%d)" % (O, T, K, P)}
+        metric = "QecModule forward samples/sec (single layer)"
+
+    elif a.config == 4:
+        # ---- configs[3]: Siamese QecSiaNet train step (train_cls_sia.py:64-79), B=16 pairs
+        B = a.batch
+        net = qb.QecSiaNet(2048, a.channels, a.classes, a.iters).to(dev)
+        bucket = ddp.FlatGradBucket(net.parameters())
+        opt = ddp.FlatAdam(bucket, lr=1e-3)
+        bucket.zero()
+        host, rots = [], []
+        for i in range(NB):
+            pts, lr, ac, lab = synthetic_batch(B, ncls=a.classes, seed=4321 + i)
+            p2, l2, a2 = siamese_pair(pts, lr, ac, seed=900 + i)
+            g = torch.Generator().manual_seed(900 + i)           # the rotation siamese_pair applied to branch 1
+            q = torch.randn(B, 1, 1, 4, generator=g)
+            q = q / q.norm(dim=-1, keepdim=True)
+            rots.append((q * torch.where(q[..., :1] < 0, -1.0, 1.0)).view(B, 4).to(dev))
+            host.append(pinned((p2, l2, a2, torch.stack([lab, lab], 1))))
+        devb = [tuple(t.to(dev) for t in hb) for hb in host]
+        static = tuple(torch.empty_like(t) for t in devb[0])
+
+        def body():
+            pose, agr = net(static[0], static[1], static[2], None)
+            total, cls, pl = net.class_pose_loss(agr, pose, static[3])   # spread x2 + 0.1 pose_diff on the GT class
+            total.backward()
+            opt.step()
+            return torch.stack([total.detach(), cls, pl])
+
+        for s_, t_ in zip(static, devb[0]):
+            s_.copy_(t_)
+        graph, out = _capture(torch, body, warm=W)
+        l0 = qb.kernel_launches()
+        body()
+        launches = qb.kernel_launches() - l0
+
+        def dev_step(i):
+            for s_, t_ in zip(static, devb[i % NB]):
+                s_.copy_(t_, non_blocking=True)
+            graph.replay() if graph is not None else body()
+
+        loss_host = torch.empty(3).pin_memory()
+
+        def e2e_step(i):
+            for s_, t_ in zip(static, host[i % NB]):
+                s_.copy_(t_, non_blocking=True)
+            o = out
+            if graph is not None:
+                graph.replay()
+            else:
+                o = body()
+            loss_host.copy_(o, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        sampler.start()
+        _time_graph(torch, dev_step, W)
+        if a.min_timed_s > 0:
+            est = _time_graph(torch, dev_step, 5)
+            a.steps = max(a.steps, int(a.min_timed_s * 1e3 / max(est, 1e-3)) + 1)
+        ms = _time_graph(torch, dev_step, a.steps)
+        ms_e2e = _time_graph(torch, e2e_step, a.steps)
+        clocks = sampler.stop()
+        # the rotation-error metric of test_rot_sia.py on the synthetic pairs (GT class, as in training)
+        from qecnetworks_b200 import eval_ops as E
+        with torch.no_grad():
+            pose_e, _ = net(devb[0][0], devb[0][1], devb[0][2], None)
+            rerr = E.relative_rotation_error(pose_e, devb[0][3][:, 0], rots[0])
+        extra["relative_rotation_error"] = {
+            "mean": float(rerr.mean()), "max": float(rerr.max()), "unit": "(2/pi) rad, q_distance of test_rot_sia.py:32-41",
+            "what": "q_distance(pose_0[y], conj(q_gt) (x) pose_1[y]) over the %d synthetic pairs of batch 0 at the ground-truth "
+                    "class (the network is rotation-equivariant, so this is the FP32 noise floor of the whole net)" % B}
+        rec = kernel_pass(body)
+        kernels = kernel_records(rec, 3, a.iters, hbm_peak, fp32_peak, ms)
+        units = B
+        workload = ("configs[3]: Siamese QecSiaNet train step (two branches fwd + spread loss x2 + 0.1 pose_diff_loss on the "
+                    "GT-class poses + bwd + Adam; train_cls_sia.py shape), B=%d pairs, 256 patches x 9-NN, C=%d, %d classes, "
+                    "T=%d, branch 1 = branch 0 rotated by a random quaternion" % (B, a.channels, a.classes, a.iters))
+        h2d = sum(t.numel() * t.element_size() for t in host[0])
+        d2h = 12
+        if not a.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
+            sb = 2
+            params = {k: v.requires_grad_(True) for k, v in orc.init_net_params(a.channels, a.classes, seed=0).items()}
+            copt = torch.optim.Adam(list(params.values()), lr=1e-3)
+            cp, cl, ca, clab = [t[:sb] for t in host[0]]
+
+            def cstep():
+                copt.zero_grad()
+                pose, agr = orc.qec_sia_net_forward(params, cp, cl, ca, a.iters, noise=1e-6)
+                sel = torch.stack([pose[:, i, clab[i, 0]] for i in range(sb)], 1)
+                (orc.sia_spread_loss(agr, clab[:, 0]) + 0.1 * orc.pose_diff_loss(sel)).backward()
+                copt.step()
+
+            cstep()
+            t0 = time.perf_counter()
+            cstep()
+            dt = time.perf_counter() - t0
+            cpu = {"value": sb / dt, "unit": "pairs/s", "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": "oracle port of the reference CPU path: one Siamese train step at B=%d pairs after a warm-up "
+                             "(per-pair cost is flat in B)" % sb}
+        final = float(out[0])
+        cfg_extra = {"loss": "spread(branch 0) + spread(branch 1) + 0.1 * pose_diff(GT-class poses), one launch (qec_class_pose_loss)"}
+        metric = "QEC-SiaNet pairs/sec fwd+bwd"
+
+    else:
+        # ---- configs[4]: routing stress sweep, B=1024 inference, P=64, I=1: corners of K x O x T
+        B, P = a.batch, 64
+        corners = [(K, O, T) for K in (9, 64) for O in (32, 512) for T in (1, 10)]
+        rows = []
+        tot_ms = tot_e2e = 0.0
+        launches = 0
+        h2d_tot = d2h_tot = 0
+        kernels = []
+        sampler.start()
+        nrep = max(1, min(a.steps, 5))
+        for (K, O, T) in corners:
+            mod = qb.QecModule(1, O, num_iterations=T, num_neighbours=K, num_patches=P).to(dev)
+            pts, lr, ac, _ = synthetic_batch(B, P=P, K=K, seed=77 + K)
+            hb = pinned((pts, lr.unsqueeze(-2).contiguous(), ac.unsqueeze(-1).contiguous()))
+            static = tuple(t.to(dev) for t in hb)
+
+            def body():
+                with torch.no_grad():
+                    return mod(*static)
+
+            graph, out = _capture(torch, body, warm=2)
+            l0 = qb.kernel_launches()
+            body()
+            launches += qb.kernel_launches() - l0
+            res_host = pinned((torch.empty(out[0].shape), torch.empty(out[1].shape)))
+
+            def dev_step(i):
+                graph.replay() if graph is not None else body()
+
+            def e2e_step(i):
+                for s_, t_ in zip(static, hb):
+                    s_.copy_(t_, non_blocking=True)
+                o = out
+                if graph is not None:
+                    graph.replay()
+                else:
+                    o = body()
+                res_host[0].copy_(o[0], non_blocking=True)
+                res_host[1].copy_(o[1], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
+            ms_c = _time_graph(torch, dev_step, nrep)
+            ms_e = _time_graph(torch, e2e_step, nrep)
+            rec = kernel_pass(body, 2)
+            ks = kernel_records(rec, 2, T, hbm_peak, fp32_peak, ms_c)
+            top = ks[0] if ks else None
+            rows.append({"K": K, "O": O, "T": T, "votes": B * P * O * K, "ms": ms_c, "samples_per_s": B / (ms_c * 1e-3),
+                         "e2e_ms": ms_e, "kernel": top and top["kernel"], "kernel_ms": top and top["ms"],
+                         "fp32_frac": top and top["fp32_frac"], "hbm_frac": top and top["hbm_frac"],
+                         "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30})
+            tot_ms += ms_c
+            tot_e2e += ms_e
+            h2d_tot += sum(t.numel() * t.element_size() for t in hb)
+            d2h_tot += sum(t.numel() * 4 for t in res_host)
+            if top is not None and (not kernels or top["ms"] > kernels[0]["ms"]):
+                kernels = ks
+            del mod, static, res_host, graph, out
+            torch.cuda.empty_cache()
+        clocks = sampler.stop()
+        ms, ms_e2e = tot_ms / len(corners), tot_e2e / len(corners)
+        units = B
+        extra["sweep"] = rows
+        workload = ("configs[4]: routing stress sweep, inference, B=%d, P=64, in_channels=1: corners K in {9,64} x O in "
+                    "{32,512} x T in {1,10}; a step = one forward of one corner, value = B / mean corner time" % B)
+        h2d, d2h = h2d_tot // len(corners), d2h_tot // len(corners)  # mean over the corners
+        a.steps = nrep
+        final = None
+        cfg_extra = {"corners": len(corners), "largest_corner_votes": B * P * 512 * 64}
+        metric = "QecModule forward samples/sec (stress sweep mean)"
+        if not a.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
+            sb = 8
+            K, O, T = 9, 512, 1
+            p = orc.init_module_params(1, O, seed=0)
+            pts, lr, ac, _ = synthetic_batch(sb, P=P, K=K, seed=5)
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                orc.qec_module_forward(p, pts, lr.unsqueeze(-2), ac.unsqueeze(-1), T, noise=1e-6)
+            dt = time.perf_counter() - t0
+            cpu = {"value": sb / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": "oracle port, ONE corner only (K=9, O=512, T=1) at B=%d, one forward: the CPU path materialises "
+                             "three [Nv,4,4] temporaries per iteration and cannot run the large corners" % sb}
+
+    roofline = roofline_of(kernels[0], hbm_peak, peak_src, fp32_peak) if kernels else None
+    out_json = {
+        "metric": metric, "value": units / (ms * 1e-3), "unit": "pairs/s" if a.config == 4 else UNIT, "n_gpus": 1,
+        "steps": a.steps, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict({"workload": workload, "global_batch": units, "parallelism": "dp1", "cuda_graph": True,
+                        "l2": "inputs are rotated over %d distinct batches; the timed kernels stream far more than the "
+                              "126 MB L2 per step except in config 1 (11 MB working set: an L2-resident latency "
+                              "measurement by nature)" % NB}, **cfg_extra),
+        "clocks": clocks,
+        "e2e": {"value": units / (ms_e2e * 1e-3), "unit": "pairs/s" if a.config == 4 else UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "what": "serial: inputs copied from pinned host memory, the step, results copied back and synchronised, every step"},
+        "gpu_launches": launches * a.steps, "gpu_launches_per_step": launches,
+        "roofline": roofline, "fp32_peak_tflops": fp32_peak, "cpu_baseline": cpu, "kernels": kernels, "final_loss": final,
+    }
+    out_json.update(extra)
+    print(json.dumps(out_json), flush=True)
+
+
 def main():
     a = parse_args()
     # stdout carries exactly ONE JSON line: anything libraries print there while the run is in flight
@@ -577,8 +1001,10 @@ def main():
     sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if a.impl == "reference":
         run_reference(a)
-    else:
+    elif a.config == 2:
         run_b200(a)
+    else:
+        run_other_config(a)
 
 
 if __name__ == "__main__":

@@ -99,11 +99,14 @@ int qec_routing_fused_bwd(const float* t_oqi, const float* lrfs, const float* ac
                           const float* g_agreement, float* g_toqi, float* g_lrfs, float* g_act, float* g_alpha_beta,
                           int BP, int K, int I, int O, int T, void* stream);
 
-/* Register-resident variant for in_channels = 1 and K <= 16 neighbours (the pool1 layer): the
+/* Composed-weight variant for in_channels = 1 (the pool1 layer; BASELINE config 5's stress geometry): the
  * two Linears of get_votes have no non-linearity between them (models/qec_module.py:123-124), so
  * t_raw = Wc x + bc with Wc = W2 W1 [4*O,3], bc = W2 b1 + b2 [4*O] (row q*O + o) composed by the
  * caller; the kernel covers qec_module.py:123-147 and 172-194 without the [BP*K, 4*O] tensor.
  *   xrot [BP,K,3] (from qec_lrf_mean_fwd), lrfs [BP,K,4], act [BP,K]
+ * qec_routing_small_supported: 1 = K <= 16, votes register-resident, forward and backward; 2 = 16 < K <= 64,
+ * forward only, votes regenerated in every sweep (nothing of the size of the vote tensor exists); 0 = not served.
+ * poses_all [T,BP,O,4] and stats [BP,O,2] are what the backward reads: both may be NULL in the forward (inference).
  * Backward: only parameter gradients (g_Wc [4*O,3], g_bc [4*O], g_alpha_beta [2], all ACCUMULATED);
  * callers that need dL/dlrfs, dL/dact or dL/dpoints use qec_votes_* + qec_routing_*. */
 int qec_routing_small_supported(int K, int I, int O, int T);

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kST)
             const Sym4 m = acc_to_sym(acc, 1.f / fmaxf(acc[10], 1e-12f));
             p = qfix(top_eigvec_weighted2(m, acc[12] != acc[10], WarpDone()));
             if (!valid) p = qmake(0.f, 0.f, 0.f, 0.f);
-            if (active) stq(poses_all + ((size_t)t * Nc + c) * 4, p);
+            if (active && poses_all != nullptr) stq(poses_all + ((size_t)t * Nc + c) * 4, p);
             if (t == T - 1) break;
             zero_acc(acc);
 #pragma unroll
@@ -138,8 +138,93 @@ __global__ void __launch_bounds__(kST)
             const float s = (n > 0.f) ? ssum / n : 0.f;
             stq(pose + c * 4, p);
             agreement[c] = (n > 0.f) ? sigmoidf(fmaf(alpha, s, beta - 1.f)) : 0.f;
-            stats[2 * c] = s;
-            stats[2 * c + 1] = n;
+            if (stats != nullptr) {
+                stats[2 * c] = s;
+                stats[2 * c + 1] = n;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Forward for 16 < K <= 64 (BASELINE config 5: the stress sweep runs K up to 64 at I = 1, inference only).
+// Sixty-four votes do not fit the register file, and parking them in shared memory (20 B per vote and
+// thread: 160 KB per CTA of 128 threads at K = 64) would leave one CTA of four warps per SM.  A vote is cheap
+// to REGENERATE instead -- 12 FMA for the composed transform, a normalisation and one Hamilton product from
+// the patch's staged LRFs / points, which every output channel shares -- so each sweep recomputes its votes
+// and only the routing weights b^t live in shared memory ([K][128] floats, thread-contiguous: conflict-free).
+// ~2x the arithmetic of a stored-vote sweep at 8 resident CTAs per SM instead of 1; nothing of the size of the
+// vote tensor (34 GB at the largest corner of the sweep) or of t_raw exists.  Same results as the
+// register-resident kernel (same per-vote code, same accumulation order over k).
+// ------------------------------------------------------------------------------------
+template <int KMAX>
+__global__ void __launch_bounds__(kST)
+    routing_small_regen_fwd_kernel(const float* __restrict__ xrot, const float* __restrict__ lrfs,
+                                   const float* __restrict__ act, const float* __restrict__ Wc,
+                                   const float* __restrict__ bc, const float* __restrict__ alpha_p,
+                                   const float* __restrict__ beta_p, float* __restrict__ pose,
+                                   float* __restrict__ agreement, float* __restrict__ poses_all,
+                                   float* __restrict__ stats, int BP, int K, int O, int T) {
+    __shared__ PatchStage<KMAX> st;
+    extern __shared__ float sbw[];  // [K][kST] routing weights b^t of this thread's capsule
+    float* bw = sbw + threadIdx.x;
+    const int o_raw = blockIdx.y * kST + threadIdx.x;
+    const bool active = o_raw < O;
+    const int o = active ? o_raw : O - 1;
+    ComposedRow cr;
+    cr.load(Wc, bc, o, O);
+    const float alpha = __ldg(alpha_p), beta = __ldg(beta_p);
+    const size_t Nc = (size_t)BP * O;
+    for (long long bp = blockIdx.x; bp < BP; bp += gridDim.x) {
+        stage_patch(st, xrot, lrfs, act, bp, K);
+        float acc[13];
+        zero_acc(acc);
+#pragma unroll 2
+        for (int k = 0; k < K; ++k) {
+            const Quat v = make_vote(q_from(st.lrf[k]), cr.apply(st.x[k])).vote;
+            const float b = st.a[k];
+            bw[k * kST] = b;
+            acc[10] += fabsf(b);
+            acc[12] += b;
+            acc_rank1(acc, b, v);
+            acc[11] += (v.w + v.x) + (v.y + v.z);
+        }
+        const bool valid = acc[11] != 0.f;
+        const size_t c = (size_t)bp * O + o;
+        Quat p;
+        for (int t = 0;; ++t) {
+            const Sym4 m = acc_to_sym(acc, 1.f / fmaxf(acc[10], 1e-12f));
+            p = qfix(top_eigvec_weighted2(m, acc[12] != acc[10], WarpDone()));
+            if (!valid) p = qmake(0.f, 0.f, 0.f, 0.f);
+            if (active && poses_all != nullptr) stq(poses_all + ((size_t)t * Nc + c) * 4, p);
+            if (t == T - 1) break;
+            zero_acc(acc);
+#pragma unroll 2
+            for (int k = 0; k < K; ++k) {
+                const Quat v = make_vote(q_from(st.lrf[k]), cr.apply(st.x[k])).vote;
+                const float b = bw[k * kST] * (st.a[k] * one_minus_dist(qdot(p, v)));
+                bw[k * kST] = b;
+                acc[10] += fabsf(b);
+                acc[12] += b;
+                acc_rank1(acc, b, v);
+            }
+        }
+        float ssum = 0.f, n = 0.f;
+#pragma unroll 2
+        for (int k = 0; k < K; ++k) {
+            const Quat v = make_vote(q_from(st.lrf[k]), cr.apply(st.x[k])).vote;
+            const float b = bw[k * kST];
+            ssum = fmaf(b, one_minus_dist(qdot(p, v)), ssum);
+            n += (b != 0.f) ? 1.f : 0.f;
+        }
+        if (active) {
+            const float s = (n > 0.f) ? ssum / n : 0.f;
+            stq(pose + c * 4, p);
+            agreement[c] = (n > 0.f) ? sigmoidf(fmaf(alpha, s, beta - 1.f)) : 0.f;
+            if (stats != nullptr) {
+                stats[2 * c] = s;
+                stats[2 * c + 1] = n;
+            }
         }
     }
 }
@@ -279,9 +364,11 @@ static dim3 small_grid(Kern kern, int BP, int O, PerDeviceInt& cache) {
 
 using namespace qec;
 
-// 1 if the composed-weight register-resident kernels serve this geometry (I = 1, K <= 16)
+// I = 1 geometries served by the composed-weight kernels: 1 = forward and backward (K <= 16, votes in
+// registers), 2 = forward only (16 < K <= 64, votes regenerated per sweep), 0 = not served
 extern "C" int qec_routing_small_supported(int K, int I, int O, int T) {
-    return (I == 1 && O > 0 && T >= 1 && T <= 10 && K >= 1 && small_kmax(K) > 0) ? 1 : 0;
+    if (!(I == 1 && O > 0 && T >= 1 && T <= 10 && K >= 1)) return 0;
+    return small_kmax(K) > 0 ? 1 : (K <= 64 ? 2 : 0);
 }
 
 extern "C" int qec_routing_small_fwd(const float* xrot, const float* lrfs, const float* act, const float* Wc,
@@ -292,10 +379,29 @@ extern "C" int qec_routing_small_fwd(const float* xrot, const float* lrfs, const
     QEC_CHECK_ARG(lrfs && act, 2);
     QEC_CHECK_ARG(Wc && bc, 4);
     QEC_CHECK_ARG(alpha && beta, 6);
-    QEC_CHECK_ARG(pose && agreement && poses_all && stats, 8);
+    QEC_CHECK_ARG(pose && agreement, 8);  // poses_all / stats (what the backward needs) may be NULL for inference
     QEC_CHECK_ARG(BP > 0, 12);
     QEC_CHECK_ARG(qec_routing_small_supported(K, 1, O, T), 13);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (small_kmax(K) == 0) {  // 16 < K <= 64: votes regenerated per sweep, weights in (dynamic) shared memory
+        static PerDeviceInt occr;
+        const size_t smem = (size_t)K * kST * sizeof(float);
+        const int gy = (O + kST - 1) / kST;
+        std::atomic<int>* slot = occr.slot();
+        int per_sm = slot ? slot->load(std::memory_order_relaxed) : -1;
+        if (per_sm < 0) {  // sized for the largest K, so one cached value serves every K
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, routing_small_regen_fwd_kernel<64>, kST,
+                                                              64 * kST * sizeof(float)) != cudaSuccess || per_sm < 1)
+                per_sm = 4;
+            if (slot) slot->store(per_sm, std::memory_order_relaxed);
+        }
+        int gx = (kNumSMs * per_sm) / gy;
+        if (gx < 1) gx = 1;
+        if (gx > BP) gx = BP;
+        routing_small_regen_fwd_kernel<64><<<dim3((unsigned)gx, (unsigned)gy), kST, smem, st>>>(
+            xrot, lrfs, act, Wc, bc, alpha, beta, pose, agreement, poses_all, stats, BP, K, O, T);
+        return launch_status();
+    }
     static PerDeviceInt occ9, occ16;
     const dim3 grid = (small_kmax(K) == 9) ? small_grid(routing_small_fwd_kernel<9>, BP, O, occ9)
                                            : small_grid(routing_small_fwd_kernel<16>, BP, O, occ16);
@@ -319,7 +425,7 @@ extern "C" int qec_routing_small_bwd(const float* xrot, const float* lrfs, const
     QEC_CHECK_ARG(g_pose && g_agreement, 10);
     QEC_CHECK_ARG(g_Wc && g_bc && g_alpha_beta, 12);
     QEC_CHECK_ARG(BP > 0, 15);
-    QEC_CHECK_ARG(qec_routing_small_supported(K, 1, O, T), 16);
+    QEC_CHECK_ARG(qec_routing_small_supported(K, 1, O, T) == 1, 16);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     static PerDeviceInt occ9, occ16;
     const dim3 grid = (small_kmax(K) == 9) ? small_grid(routing_small_bwd_kernel<9>, BP, O, occ9)

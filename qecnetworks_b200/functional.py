@@ -283,7 +283,6 @@ class ClassPoseLoss(torch.autograd.Function):
         launch("qec_class_pose_loss", x, labels, float(margin), pose, float(w_pose), loss, g_x, g_pose, err, S, B, C)
         ctx.save_for_backward(g_x, g_pose)
         ctx.err = err
-        ctx.mark_non_differentiable(labels)
         return loss
 
     @staticmethod
@@ -324,6 +323,9 @@ class RoutingSmall(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xrot, lrfs, activation, Wc, bc, alpha, beta, num_iterations):
+        if any(ctx.needs_input_grad) and routing_small_supported(activation.shape[2], 1, bc.shape[0] // 4,
+                                                                 num_iterations) != 1:
+            raise _lib.QecLibraryError("routing_small: K > 16 is forward-only (inference); use votes() + routing()")
         B, P, K = activation.shape
         O = bc.shape[0] // 4
         xrot = _check(xrot, "xrot", (B, P, K, 1, 3))
@@ -337,11 +339,13 @@ class RoutingSmall(torch.autograd.Function):
         dev = lrfs.device
         pose = torch.empty(B, P, O, 4, device=dev, dtype=torch.float32)
         agreement = torch.empty(B, P, O, device=dev, dtype=torch.float32)
-        poses_all = torch.empty(T, B, P, O, 4, device=dev, dtype=torch.float32)
-        stats = torch.empty(B, P, O, 2, device=dev, dtype=torch.float32)
+        saved = any(ctx.needs_input_grad)  # inference: nothing is kept for a backward (T x 16 B per capsule)
+        poses_all = torch.empty(T, B, P, O, 4, device=dev, dtype=torch.float32) if saved else None
+        stats = torch.empty(B, P, O, 2, device=dev, dtype=torch.float32) if saved else None
         launch("qec_routing_small_fwd", xrot, lrfs, activation, Wc, bc, alpha, beta,
              pose, agreement, poses_all, stats, B * P, K, O, T)
-        ctx.save_for_backward(xrot, lrfs, activation, Wc, bc, alpha, beta, poses_all, stats)
+        if saved:
+            ctx.save_for_backward(xrot, lrfs, activation, Wc, bc, alpha, beta, poses_all, stats)
         ctx.T = T
         return pose, agreement
 
@@ -365,7 +369,8 @@ class RoutingSmall(torch.autograd.Function):
 
 
 def routing_small_supported(K, I, O, T):
-    return bool(_lib.query("qec_routing_small_supported", int(K), int(I), int(O), int(T)))
+    """0 = not served, 1 = forward + backward (K <= 16), 2 = forward only (16 < K <= 64)"""
+    return int(_lib.query("qec_routing_small_supported", int(K), int(I), int(O), int(T)))
 
 
 def routing_small(xrot, lrfs, activation, Wc, bc, alpha, beta, num_iterations):

@@ -222,6 +222,11 @@ class QecModule(Module):
         self.alpha.data.fill_(1)
         self.beta.data.fill_(1)
 
+    # Inference on a large batch (BASELINE config 5: B = 1024): the paths that materialise per-vote tensors
+    # (transforms: 16 B per vote; transforms + votes: 32 B per vote) run over slices of the batch so that no
+    # temporary exceeds this many bytes.  Every capsule depends on one sample only, so slicing changes nothing.
+    INFERENCE_TEMP_BYTES = 2 << 30
+
     def forward(self, points, lrfs, activation):
         """points [B,P,K,3], lrfs [B,P,K,I,4], activation [B,P,K,I]
         -> pose [B,P,O,4] (O squeezed when 1, as the reference's pose.squeeze(-2)),
@@ -233,13 +238,28 @@ class QecModule(Module):
                 "QecModule(in=%d, K=%d, P=%d) got lrfs %s"
                 % (self.in_channels, self.num_neighbours, self.num_patches, tuple(lrfs.shape))
             )
+        if not torch.is_grad_enabled() and B > 1:
+            small = QF.routing_small_supported(K, I, O, self.num_iterations) if I == 1 else 0
+            per_sample = 0 if small else 32 * P * K * I * O  # (the cluster path needs 16: bounded by the same cap)
+            if per_sample * B > self.INFERENCE_TEMP_BYTES:
+                step = max(1, self.INFERENCE_TEMP_BYTES // per_sample)
+                outs = [self._forward(points[b:b + step], lrfs[b:b + step], activation[b:b + step])
+                        for b in range(0, B, step)]
+                return torch.cat([o[0] for o in outs], 0), torch.cat([o[1] for o in outs], 0)
+        return self._forward(points, lrfs, activation)
+
+    def _forward(self, points, lrfs, activation):
+        B, P, K, I, _ = lrfs.shape
+        O = self.out_channels
         points = points.float().contiguous()
         lrfs = lrfs.float().contiguous()
         activation = activation.float().contiguous()
         _, xrot = QF.lrf_mean_rotate(lrfs, activation, points)
         act_flat = activation.view(B, P, K * I)
         data_grad = torch.is_grad_enabled() and (points.requires_grad or lrfs.requires_grad or activation.requires_grad)
-        if I == 1 and not data_grad and QF.routing_small_supported(K, I, O, self.num_iterations):
+        param_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        small = QF.routing_small_supported(K, I, O, self.num_iterations) if I == 1 else 0
+        if not data_grad and (small == 1 or (small == 2 and not param_grad)):
             # no non-linearity between the two Linears: compose them (rank 3 for I = 1) and let the
             # register-resident kernel evaluate Wc x + bc per vote -- no [B*P*K, 4*O] tensor, no GEMM
             W1, b1 = self.quater_gen1.weight, self.quater_gen1.bias

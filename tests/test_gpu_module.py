@@ -465,3 +465,53 @@ def test_module_on_second_device_without_set_device():
         pose, agr = mod(g["points"].to("cuda:1"), g["lrfs"].to("cuda:1"), g["act"].to("cuda:1"))
     assert pose.device.index == 1 and torch.cuda.current_device() == 0
     assert quat_err(pose.cpu(), g["pose"]) < TOL and max_err(agr.cpu(), g["agreement"]) < TOL
+
+
+@pytest.mark.parametrize("K,O,T", [(9, 32, 1), (64, 512, 10), (32, 128, 3)])
+def test_stress_corners_full_batch(K, O, T):
+    """BASELINE config 5 at its stated batch (B = 1024 inference, P = 64, I = 1): corners of the sweep at full size.
+    Every capsule depends on one sample only, so three samples of the big batch are checked against the float64
+    oracle run on those samples alone; plus unit norm / hemisphere / activation range over the whole output.
+    K = 64, O = 512 is the corner whose vote tensor would be 34 GB: it runs on the regenerate-votes kernel."""
+    import qecnetworks_b200 as qb
+
+    dev = cuda()
+    B, P = 1024, 64
+    params = orc.init_module_params(1, O, seed=K + O)
+    params["quater_gen2.bias"] = params["quater_gen2.bias"] + torch.tensor([1.5, 0.2, -0.3, 0.4]).repeat_interleave(O)
+    points, lrfs, act, _ = orc.synthetic_batch(B, P=P, K=K, seed=K * 5 + T)
+    mod = qb.QecModule(1, O, num_iterations=T, num_neighbours=K, num_patches=P)
+    mod.load_state_dict(params)
+    mod = mod.to(dev)
+    before = torch.cuda.max_memory_allocated()
+    with torch.no_grad():
+        pose, agr = mod(points.to(dev), lrfs.unsqueeze(-2).to(dev), act.unsqueeze(-1).to(dev))
+    assert pose.shape == (B, P, O, 4) and agr.shape == (B, P, O)
+    # nothing of the size of the vote tensor (16 B x B P O K) was allocated
+    assert torch.cuda.max_memory_allocated() - before < 3 * pose.numel() * 4 + (1 << 30)
+    assert float((pose.norm(dim=-1) - 1).abs().max()) < 1e-5 and float(pose[..., 0].min()) >= 0.0
+    assert float(agr.min()) > 0.0 and float(agr.max()) < 1.0
+    pick = torch.tensor([0, 511, 1023])
+    p64 = {k: v.double() for k, v in params.items()}
+    pose_ref, agr_ref = orc.qec_module_forward(p64, points[pick].double(), lrfs[pick].unsqueeze(-2).double(),
+                                               act[pick].unsqueeze(-1).double(), T)
+    assert quat_err(pose[pick.to(dev)].cpu(), pose_ref) < TOL
+    assert max_err(agr[pick.to(dev)].cpu(), agr_ref) < TOL
+
+
+def test_general_path_inference_is_sliced_over_the_batch():
+    """a geometry on the general path (I > 1, few votes per capsule): under no_grad a large batch runs in slices so
+    that no per-vote temporary exceeds QecModule.INFERENCE_TEMP_BYTES, with results identical to the unsliced run"""
+    import qecnetworks_b200 as qb
+
+    dev = cuda()
+    g = load_golden("module_small")
+    mod = make_module(g, dev)
+    rep = 37
+    pts, lr, ac = [g[k].repeat(rep, *([1] * (g[k].dim() - 1))).to(dev) for k in ("points", "lrfs", "act")]
+    with torch.no_grad():
+        pose_a, agr_a = mod(pts, lr, ac)
+        mod.INFERENCE_TEMP_BYTES = 32 * 3 * 5 * 4 * 6 * 5   # five samples per slice
+        pose_b, agr_b = mod(pts, lr, ac)
+    assert torch.equal(pose_a, pose_b) and torch.equal(agr_a, agr_b)
+    assert quat_err(pose_b[-2:].cpu(), g["pose"]) < TOL
