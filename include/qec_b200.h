@@ -219,6 +219,19 @@ int qec_quat_eval(const float* pose1, const float* pose2, float* dist, float* re
  * out-of-range argument only queries.  No reference counterpart. */
 int qec_routing_fused_set_wide(int mode);
 
+/* Which generation of the packed cluster-resident kernels qec_routing_fused_fwd / _bwd dispatch to when both serve
+ * the geometry: bit 0 = forward, bit 1 = backward on the third generation (two capsules in flight per cluster, a
+ * dedicated solver warp hides the reduce -> solve -> publish chain behind the other capsule's sweep;
+ * csrc/routing_fused3.cu), else the second (csrc/routing_fused2.cu).  Same results to rounding (tests run both).
+ * Initial value from the environment (QEC_FUSED_PP).  Returns the previous mode; an out-of-range argument only
+ * queries.  qec_routing_fused_pp_fwd is the third-generation forward itself (same contract as
+ * qec_routing_fused_fwd; argument 11 if qec_routing_fused_pp_supported(...) is 0).  No reference counterpart. */
+int qec_routing_fused_set_pp(int mode);
+int qec_routing_fused_pp_supported(int K, int I, int O, int T);
+int qec_routing_fused_pp_fwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
+                             const float* beta, float* pose, float* agreement, float* poses_all, float* stats, int BP,
+                             int K, int I, int O, int T, void* stream);
+
 /* One Adam step (reference train_cls.py:44-51: torch.optim.Adam, default betas / eps) on FLAT FP32 buffers of n
  * elements, 16-byte aligned -- parameters, gradient, first and second moment (qecnetworks_b200/ddp.py lays the
  * network's tensors out as views of such buffers).  The gradient is read as grads * grad_scale (1/world after a

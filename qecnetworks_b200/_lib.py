@@ -29,6 +29,9 @@ SIGNATURES = {
     "qec_routing_fused_bwd": ([_P] * 13 + [_I, _I, _I, _I, _I, _P], 1),
     "qec_routing_fused_packed_supported": ([_I, _I, _I, _I], 0),
     "qec_routing_fused_set_wide": ([_I], 0),
+    "qec_routing_fused_set_pp": ([_I], 0),
+    "qec_routing_fused_pp_supported": ([_I, _I, _I, _I], 0),
+    "qec_routing_fused_pp_fwd": ([_P] * 9 + [_I, _I, _I, _I, _I, _P], 1),
     "qec_routing_fused_bwd_split": ([_P] * 14 + [_I, _I, _I, _I, _I, _P], 1),
     "qec_routing_fused_fwd_scalar": ([_P] * 9 + [_I, _I, _I, _I, _I, _P], 1),
     "qec_routing_fused_bwd_scalar": ([_P] * 13 + [_I, _I, _I, _I, _I, _P], 1),

@@ -124,10 +124,26 @@ __device__ __forceinline__ Quat2 qham2_conjl(const Quat2& q, const Quat2& r) {
     return o;
 }
 
-// 1 - d(x) for both halves; bit-identical per half to one_minus_dist (qec_math.cuh): the
-// polynomial is evaluated with negated coefficients so the final fma needs no negation.
+// 1 - d(x) for both halves.  Default (QEC_ESTRIN = 1): the Estrin form of the polynomial, dependency depth 3 instead
+// of 8 -- bit-identical per half to one_minus_dist_estrin (qec_math.cuh).  QEC_ESTRIN = 0: the Horner form,
+// bit-identical per half to one_minus_dist.  Negated coefficients so the final fma needs no negation.
+#ifndef QEC_ESTRIN
+#define QEC_ESTRIN 0
+#endif
 __device__ __forceinline__ f2 one_minus_dist2(f2 x) {
     const f2 y = pk(fminf(fabsf(lo(x)), QEC_DCLAMP), fminf(fabsf(hi(x)), QEC_DCLAMP));
+#if QEC_ESTRIN
+    const f2 y2 = mul2(y, y), y4 = mul2(y2, y2);
+    const f2 a = fma2(bc(0.1366178402f), y, bc(-0.9999999861f));
+    const f2 b = fma2(bc(0.0319419544f), y, bc(-0.0566457827f));
+    const f2 c = fma2(bc(0.0108786386f), y, bc(-0.0196663823f));
+    const f2 d = fma2(bc(0.0008037268f), y, bc(-0.0042463112f));
+    const f2 ab = fma2(b, y2, a), cd = fma2(d, y2, c);
+    const f2 pe = fma2(cd, y4, ab);
+    const f2 ome = fma2(y, bc(-1.f), bc(1.f));
+    const f2 se = pk(fsqrt_fast(lo(ome)), fsqrt_fast(hi(ome)));
+    return fma2(se, pe, bc(1.f));
+#endif
     f2 p = fma2(bc(0.0008037268f), y, bc(-0.0042463112f));
     p = fma2(p, y, bc(0.0108786386f));
     p = fma2(p, y, bc(-0.0196663823f));

@@ -139,6 +139,22 @@ QEC_HD float one_minus_dist(float x) {
     return fmaf(-fsqrt_fast(1.f - y), p, 1.f);
 }
 
+// The same polynomial in Estrin form: dependency depth 3 instead of 8 (one more multiply).  The cluster kernels
+// (f32x2.cuh: one_minus_dist2) use it because a sweep is a chain dot -> distance -> weight -> accumulate per vote
+// pair and the Horner recurrence alone was 8 dependent FFMA2 of it; rounding differs from the Horner form by
+// ~1 ulp of the result (tests/test_host_math.py checks both against float64).
+QEC_HD float one_minus_dist_estrin(float x) {
+    const float y = fminf(fabsf(x), QEC_DCLAMP);
+    const float y2 = y * y, y4 = y2 * y2;
+    const float a = fmaf(-0.1366178402f, y, 0.9999999861f);
+    const float b = fmaf(-0.0319419544f, y, 0.0566457827f);
+    const float c = fmaf(-0.0108786386f, y, 0.0196663823f);
+    const float d = fmaf(-0.0008037268f, y, 0.0042463112f);
+    const float ab = fmaf(b, y2, a), cd = fmaf(d, y2, c);
+    const float p = fmaf(cd, y4, ab);
+    return fmaf(-fsqrt_fast(1.f - y), p, 1.f);
+}
+
 // d/dx of d(x): -(2/pi) sign(x) / sqrt(1 - x^2) where |x| <= 0.9999, else 0
 // (torch: abs -> sign(x), clamp(max) passes the gradient where |x| <= max)
 QEC_HD float dist_grad(float x) {

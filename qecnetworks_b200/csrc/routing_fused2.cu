@@ -34,9 +34,7 @@
 
 #include <cstdlib>
 
-#include "f32x2.cuh"
-#include "routing_core.cuh"
-#include "routing_fused_shared.cuh"
+#include "routing_pair.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -50,6 +48,41 @@ namespace cg = cooperative_groups;
 #ifndef QEC_VARIANT_NS
 #define QEC_VARIANT_NS pt256
 #endif
+// Software-pipelined shared-memory operands (1 = on, the default; 0 = the previous schedule, kept for A/B timing).
+// Every sweep both reads its slot (votes, activation, weight) and writes shared memory for it (the updated weight,
+// the regenerated vote, or -- through cp.async, a compiler barrier -- the next capsule's transforms).  The compiler
+// cannot prove that those stores do not alias the NEXT slot's loads, so it issued slot m+1's LDS only after slot m's
+// whole dependent chain (dot -> distance polynomial -> weight -> STS) had retired: one slot in flight per warp, ~300
+// cycles per pair and sweep against ~65 cycles of fma-pipe work (ncu source page, profiles/r01_fused2_ncu.txt: the
+// first instruction after each LDS.128 carries the short-scoreboard stalls, every Horner step a fixed-latency wait).
+// QEC_SWP is a bit mask of the sweeps that use it: 1 forward routing sweeps, 2 forward sweep 0, 4 forward epilogue,
+// 8 backward accumulation sweeps, 16 backward sweep 0.
+// With QEC_SWP the operands of slot m+1 are loaded into registers BEFORE slot m is computed and stored, so two
+// slots' chains overlap inside each warp.  Same arithmetic in the same order: results are bit-identical.
+#ifndef QEC_SWP
+#define QEC_SWP 0
+#endif
+// Order in which the persistent clusters walk over the capsules.  0: capsule c = bp * O + o in memory order, so
+// the ~33 clusters in flight work on the O capsules of ONE patch at a time (its LRFs / activations are shared:
+// L1/L2-friendly) -- but in the backward they then all add into the SAME dL/dlrfs rows at about the same time, and
+// the L2 atomic unit serialises per address.  1: walk o-major (u -> bp = u % BP, o = u / BP), so concurrent
+// clusters sit on different patches: no same-address contention, LRFs / activations come from L2 (20 MB working
+// set for 32 patches).
+#ifndef QEC_SPREAD
+#define QEC_SPREAD 0
+#endif
+#ifndef QEC_PP_DEFAULT
+#define QEC_PP_DEFAULT 0
+#endif
+__device__ __forceinline__ long long caps_of(long long u, long long BPn, int O) {
+#if QEC_SPREAD
+    const long long o = u / BPn;
+    return (u - o * BPn) * O + o;
+#else
+    (void)BPn; (void)O;
+    return u;
+#endif
+}
 
 namespace qec {
 namespace QEC_VARIANT_NS {
@@ -77,35 +110,6 @@ constexpr int kCtasPerSM = (kPT <= 256) ? 2 : 1;
 constexpr int kPairs = 8;        // resident vote pairs per thread
 constexpr int kNpMax = kPT * kPairs;  // 2048 pairs = 4096 votes per CTA
 
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-__device__ __forceinline__ Quat2 lds_pair(const float4* sA, const float4* sB, int ps) {
-    const float4 a = sA[ps], b = sB[ps];
-    Quat2 v;
-    v.w = pk(a.x, a.y); v.x = pk(a.z, a.w); v.y = pk(b.x, b.y); v.z = pk(b.z, b.w);
-    return v;
-}
-__device__ __forceinline__ void sts_pair(float4* sA, float4* sB, int ps, const Quat2& v) {
-    sA[ps] = make_float4(lo(v.w), hi(v.w), lo(v.x), hi(v.x));
-    sB[ps] = make_float4(lo(v.y), hi(v.y), lo(v.z), hi(v.z));
-}
-__device__ __forceinline__ f2 lds_f2(const float2* p) {
-    const float2 v = *p;
-    return pk(v.x, v.y);
-}
-__device__ __forceinline__ void sts_f2(float2* p, f2 v) { *p = make_float2(lo(v), hi(v)); }
-__device__ __forceinline__ f2 ldg_f2(const float* p) {
-    const float2 v = __ldg(reinterpret_cast<const float2*>(p));
-    return pk(v.x, v.y);
-}
 
 
 // ------------------------------------------------------------------------------------
@@ -125,21 +129,6 @@ __device__ __forceinline__ f2 ldg_f2(const float* p) {
 // too: 8x the remote stores make the wait for the totals longer than the barrier it saves,
 // forward 0.51 -> 0.64 ms.)
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
-    unsigned r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void st_async_f32(unsigned remote_addr, float v, unsigned remote_mbar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
-                 "r"(__float_as_uint(v)), "r"(remote_mbar)
-                 : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
 template <int CL>
 struct PushReducer {
     static constexpr int NT = kPT;
@@ -163,6 +152,9 @@ struct PushReducer {
     __device__ __forceinline__ void reduce(float (&a)[N], int evt = 0, int prof_n = 64) {
         static_assert(N <= kRows, "accumulator too wide");
         (void)evt; (void)prof_n;
+#ifdef QEC_PROBE_NOCHAIN  // timing probe only (wrong results): what the sweeps alone cost, no reduce / solve / broadcast
+        return;
+#endif
         const int tid = threadIdx.x;
         // phase n uses receive buffer / mbarrier n & 1.  A peer can be at most one phase ahead, so a
         // push of phase n + 1 never lands in the mbarrier that still collects phase n.
@@ -215,6 +207,15 @@ struct PushReducer {
         QEC_EVT(evt + 2);
         ++phase;
     }
+#ifdef QEC_PROBE_NOCHAIN
+    __device__ __forceinline__ bool solver() const { return false; }
+    template <int N>
+    __device__ __forceinline__ void bcast(float (&r)[N]) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) r[i] = 0.5f;
+    }
+    __device__ __forceinline__ void sync() {}
+#else
     __device__ __forceinline__ bool solver() const { return threadIdx.x < 32; }
     template <int N>
     __device__ __forceinline__ void bcast(float (&r)[N]) {
@@ -229,60 +230,8 @@ struct PushReducer {
     // a reduction whose result only warp 0 consumes still needs the CTA to stay behind the solver
     // before scr is reused: callers follow it with bcast() or sync()
     __device__ __forceinline__ void sync() { __syncthreads(); }
+#endif
 };
-
-// round-to-nearest onto the TF32 grid (10-bit mantissa), both halves; the result is exactly representable
-__device__ __forceinline__ f2 tf32_round2(f2 v) {
-    const unsigned a = (__float_as_uint(lo(v)) + 0x1000u) & 0xffffe000u, b = (__float_as_uint(hi(v)) + 0x1000u) & 0xffffe000u;
-    return pk(__uint_as_float(a), __uint_as_float(b));
-}
-
-// (lo, hi) -> two BF16 (round to nearest even) in one word, lo at the lower address
-__device__ __forceinline__ unsigned bf16x2(f2 v) {
-    unsigned d;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi(v)), "f"(lo(v)));
-    return d;
-}
-
-// two votes at once (reference models/qec_module.py:129-145, scalar twin: make_vote in vote_math.cuh)
-struct VotePair {
-    Quat2 vote;
-    Quat2 that;  // normalised transform before the hemisphere fix
-    Quat2 t;     // fix(that)
-    f2 rn, st, sv;
-};
-// sign(x) with sign(0) = 0 as clamp(x * 2^126, -1, 1): exact for every normal x (denormals are
-// flushed to zero by -ftz, like in the comparisons of fsign); 1 FMUL2 + 4 FMNMX per pair
-__device__ __forceinline__ f2 sign2(f2 x) {
-    const f2 y = mul2(x, bc(8.507059173e37f));
-    return pk(fminf(fmaxf(lo(y), -1.f), 1.f), fminf(fmaxf(hi(y), -1.f), 1.f));
-}
-__device__ __forceinline__ float rnorm_eps(float n2) { return (n2 > 1e-24f) ? frsqrt(n2) : 1e12f; }
-
-template <bool kKeepParts>
-__device__ __forceinline__ VotePair make_vote2(const Quat2& lrf, const Quat2& traw) {
-    VotePair r;
-    const f2 n2 = qdot2(traw, traw);
-    r.rn = pk(rnorm_eps(lo(n2)), rnorm_eps(hi(n2)));  // x / max(|x|, eps)
-    const f2 thw = mul2(traw.w, r.rn);
-    if (kKeepParts) {
-        r.st = sign2(thw);
-        r.that = qscale2(traw, r.rn);
-        r.t = qscale2(r.that, r.st);
-        const Quat2 h = qham2(lrf, r.t);
-        r.sv = sign2(h.w);
-        r.vote = qscale2(h, r.sv);
-    } else {
-        // fix(l (x) fix(that)) == fix(l (x) that) unless that.w == 0 (then the vote is zeroed): a sign
-        // flip of t flips the product exactly and the outer hemisphere fix absorbs it
-        r.that.w = thw; r.that.x = mul2(traw.x, r.rn); r.that.y = mul2(traw.y, r.rn); r.that.z = mul2(traw.z, r.rn);
-        const Quat2 h = qham2(lrf, r.that);
-        const f2 s = sign2(h.w);
-        r.sv = pk((lo(thw) != 0.f) ? lo(s) : 0.f, (hi(thw) != 0.f) ? hi(s) : 0.f);
-        r.vote = qscale2(h, r.sv);
-    }
-    return r;
-}
 
 
 // ------------------------------------------------------------------------------------
@@ -308,15 +257,6 @@ __device__ __forceinline__ void prefetch_slot(const PairGeom& G, const float* tc
         cp_async8(b + 2, tp + 3 * G.I);
     }
     cp_async_commit();
-}
-
-// acc: M (10), [10] = sum |b|, [11] = sum b.  All 32 lanes of the solving warp hold the same sums,
-// so the convergence branch of the low-latency solver is uniform without a vote.
-__device__ __forceinline__ Quat solve_pose2(const float* acc, bool valid) {
-    const Sym4 m = acc_to_sym(acc, 1.f / fmaxf(acc[10], 1e-12f));  // F.normalize(p=1) of the weights
-    Quat p = qfix(top_eigvec_weighted2(m, acc[11] != acc[10], ThreadDone()));
-    if (!valid) p = qmake(0.f, 0.f, 0.f, 0.f);
-    return p;
 }
 
 template <int M>
@@ -366,8 +306,9 @@ __global__ void __launch_bounds__(kPT, kCtasPerSM)
     };
     auto live = [&](int m) { return FULL || (threadIdx.x + m * kPT < G.np); };
 
+    const long long BPn = Nc / O;
     if (cid < Nc) {
-        const float* tc = tcap_of(cid);
+        const float* tc = tcap_of(caps_of(cid, BPn, O));
 #pragma unroll
         for (int m = 0; m < kPairs; ++m) prefetch_slot<FULL>(G, tc, sA, sB, m);
     }
@@ -387,7 +328,8 @@ __global__ void __launch_bounds__(kPT, kCtasPerSM)
         stats[2 * c + 1] = en;
     };
 
-    for (long long c = cid; c < Nc; c += ncl) {
+    for (long long u = cid; u < Nc; u += ncl) {
+        const long long c = caps_of(u, BPn, O);
         const long long bp = c / O;
         const float* lrf_c = lrfs + ((size_t)bp * J + j_begin) * 4;
         const float* act_c = act + (size_t)bp * J + j_begin;
@@ -399,9 +341,8 @@ __global__ void __launch_bounds__(kPT, kCtasPerSM)
             float sabs = 0.f;
 #pragma unroll
             for (int i = 0; i < 10; ++i) m2[i] = bc(0.f);
-            auto gen = [&](int m, const Quat2& lrf, f2 a) {
+            auto gen_t = [&](int m, const Quat2& lrf, f2 a, const Quat2& traw) {
                 const int ps = threadIdx.x + m * kPT;
-                const Quat2 traw = lds_pair(sA, sB, ps);
                 const Quat2 v = make_vote2<false>(lrf, traw).vote;
                 sts_pair(sA, sB, ps, v);
                 sts_f2(sa + ps, a);
@@ -411,6 +352,7 @@ __global__ void __launch_bounds__(kPT, kCtasPerSM)
                 acc_rank1_2(m2, a, v);
                 comp = add2(comp, add2(add2(v.w, v.x), add2(v.y, v.z)));
             };
+            auto gen = [&](int m, const Quat2& lrf, f2 a) { gen_t(m, lrf, a, lds_pair(sA, sB, threadIdx.x + m * kPT)); };
             auto ldl = [&](int m, Quat2& lrf, f2& a) {  // the pair's LRFs and activations (L2-resident: shared by all O)
                 const int ps = threadIdx.x + m * kPT;
                 if (live(m)) {
@@ -423,10 +365,24 @@ __global__ void __launch_bounds__(kPT, kCtasPerSM)
             f2 av[3];
             ldl(0, lr[0], av[0]);
             ldl(1, lr[1], av[1]);
+#if (QEC_SWP & 2)
+            // the transforms of slot M+1 leave shared memory before slot M is generated and stored
+            Quat2 tr[2];
+            wait_slot<0>();
+            if (live(0)) tr[0] = lds_pair(sA, sB, threadIdx.x);
+#define QEC_GEN_SLOT(M)                                                                        \
+    if ((M) + 2 < kPairs) ldl((M) + 2, lr[((M) + 2) % 3], av[((M) + 2) % 3]);                  \
+    if ((M) + 1 < kPairs) {                                                                    \
+        wait_slot<((M) + 1 < kPairs ? (M) + 1 : 0)>();                                         \
+        if (live((M) + 1)) tr[((M) + 1) & 1] = lds_pair(sA, sB, threadIdx.x + ((M) + 1) * kPT); \
+    }                                                                                          \
+    if (live(M)) gen_t((M), lr[(M) % 3], av[(M) % 3], tr[(M) & 1]);
+#else
 #define QEC_GEN_SLOT(M)                                                       \
     if ((M) + 2 < kPairs) ldl((M) + 2, lr[((M) + 2) % 3], av[((M) + 2) % 3]); \
     wait_slot<(M)>();                                                         \
     if (live(M)) gen((M), lr[(M) % 3], av[(M) % 3]);
+#endif
             QEC_GEN_SLOT(0) QEC_GEN_SLOT(1) QEC_GEN_SLOT(2) QEC_GEN_SLOT(3)
             QEC_GEN_SLOT(4) QEC_GEN_SLOT(5) QEC_GEN_SLOT(6) QEC_GEN_SLOT(7)
 #undef QEC_GEN_SLOT
@@ -463,6 +419,33 @@ __global__ void __launch_bounds__(kPT, kCtasPerSM)
             float sabs = 0.f;
 #pragma unroll
             for (int i = 0; i < 10; ++i) m2[i] = bc(0.f);
+#if (QEC_SWP & 1)
+            Quat2 vn;
+            f2 an = bc(0.f), bn = bc(0.f);
+            auto lds_slot = [&](int m) {
+                const int ps = threadIdx.x + m * kPT;
+                if (live(m)) {
+                    vn = lds_pair(sA, sB, ps);
+                    an = lds_f2(sa + ps);
+                    bn = lds_f2(sb + ps);
+                }
+            };
+            lds_slot(0);
+#pragma unroll
+            for (int m = 0; m < kPairs; ++m) {
+                const int ps = threadIdx.x + m * kPT;
+                const Quat2 v = vn;
+                const f2 a = an, b0 = bn;
+                if (m + 1 < kPairs) lds_slot(m + 1);  // before this slot's store: the next chain starts under this one
+                if (live(m)) {
+                    const f2 b = mul2(b0, mul2(a, one_minus_dist2(qdot2(p, v))));
+                    sts_f2(sb + ps, b);
+                    sabs = (sabs + fabsf(lo(b))) + fabsf(hi(b));
+                    ssum = add2(ssum, b);
+                    acc_rank1_2(m2, b, v);
+                }
+            }
+#else
 #pragma unroll
             for (int m = 0; m < kPairs; ++m) {
                 const int ps = threadIdx.x + m * kPT;
@@ -476,6 +459,7 @@ __global__ void __launch_bounds__(kPT, kCtasPerSM)
                     acc_rank1_2(m2, b, v);
                 }
             }
+#endif
             float a2[12];
 #pragma unroll
             for (int i = 0; i < 10; ++i) a2[i] = hsum(m2[i]);
@@ -500,11 +484,33 @@ __global__ void __launch_bounds__(kPT, kCtasPerSM)
         // ---- epilogue sweep (reference qec_module.py:188-193); each slot is refilled with the next
         // capsule's transforms as soon as its vote has been read
         {
-            const long long cn = c + ncl;
-            const bool more = cn < Nc;
-            const float* tn = more ? tcap_of(cn) : t_oqi;
+            const bool more = u + ncl < Nc;
+            const float* tn = more ? tcap_of(caps_of(u + ncl, BPn, O)) : t_oqi;
             f2 es = bc(0.f);
             float en = 0.f;
+#if (QEC_SWP & 4)
+            Quat2 vn;
+            f2 bn = bc(0.f);
+            auto lds_slot = [&](int m) {
+                const int ps = threadIdx.x + m * kPT;
+                if (live(m)) {
+                    vn = lds_pair(sA, sB, ps);
+                    bn = lds_f2(sb + ps);
+                }
+            };
+            lds_slot(0);
+#pragma unroll
+            for (int m = 0; m < kPairs; ++m) {
+                const Quat2 v = vn;
+                const f2 b = bn;
+                if (m + 1 < kPairs) lds_slot(m + 1);  // ahead of the cp.async below (a compiler barrier)
+                if (more) prefetch_slot<FULL>(G, tn, sA, sB, m);  // slot m is in registers: refill it right away
+                if (live(m)) {
+                    es = fma2(b, one_minus_dist2(qdot2(p, v)), es);
+                    en += ((lo(b) != 0.f) ? 1.f : 0.f) + ((hi(b) != 0.f) ? 1.f : 0.f);
+                }
+            }
+#else
 #pragma unroll
             for (int m = 0; m < kPairs; ++m) {
                 const int ps = threadIdx.x + m * kPT;
@@ -516,6 +522,7 @@ __global__ void __launch_bounds__(kPT, kCtasPerSM)
                 }
                 if (more) prefetch_slot<FULL>(G, tn, sA, sB, m);
             }
+#endif
             e0 = hsum(es);
             e1 = en;
             pend = true;
@@ -603,58 +610,6 @@ static int launch_fused2_fwd(const float* t_oqi, const float* lrfs, const float*
 // level.  The transforms of the next capsule are prefetched into the vote slots during the last
 // sweep, as in the forward.
 // ------------------------------------------------------------------------------------
-struct Bwd2Caps {  // per-capsule state, registers
-    Quat ph[kTB], uh[kTB];
-    float rS[kTB];
-    float gsn;
-};
-
-// g = dL/dvote -> dL/dt_raw, dL/dlrf for a pair (scalar twin: vote_bwd in vote_math.cuh)
-__device__ __forceinline__ void vote_bwd2(const Quat2& lrf, const VotePair& vp, const Quat2& g, Quat2& g_traw,
-                                          Quat2& g_lrf) {
-    const Quat2 gh = qscale2(g, vp.sv);
-    g_lrf = qham2_conjr(gh, vp.t);                            // d(l (x) t)/dl = g (x) conj(t)
-    const Quat2 gt = qscale2(qham2_conjl(lrf, gh), vp.st);    // d(l (x) t)/dt = conj(l) (x) g, through the fix
-    // normalisation Jacobian (I - that that^T) / |t_raw|   (identity / eps if clamped)
-    const f2 d = qdot2(vp.that, gt);
-    const f2 proj = pk((lo(vp.rn) < 1e12f) ? lo(d) : 0.f, (hi(vp.rn) < 1e12f) ? hi(d) : 0.f);
-    const f2 np = mul2(proj, bc(-1.f));
-    g_traw.w = mul2(fma2(np, vp.that.w, gt.w), vp.rn);
-    g_traw.x = mul2(fma2(np, vp.that.x, gt.x), vp.rn);
-    g_traw.y = mul2(fma2(np, vp.that.y, gt.y), vp.rn);
-    g_traw.z = mul2(fma2(np, vp.that.z, gt.z), vp.rn);
-}
-
-// gradient w.r.t. b^TT (gb), running activation gradient (ga), b^t of all levels, <p^TT,v>, <u^TT,v>
-template <int T, int TT>
-__device__ __forceinline__ void complete_levels2(const Bwd2Caps& C, const Quat2& v, f2 a, f2 gate, f2 om0, f2 om1,
-                                                 f2& gb, f2& ga, f2& x_tt, f2& uv_tt, f2 (&b)[kTB]) {
-    b[0] = a;
-    b[1] = mul2(a, mul2(a, om0));
-    b[2] = mul2(b[1], mul2(a, om1));
-    gb = bc(0.f);
-    ga = bc(0.f);
-#pragma unroll
-    for (int t = T - 1; t >= TT; --t) {
-        const f2 x = qdot2(C.ph[t], v);
-        const f2 uv = qdot2(C.uh[t], v);
-        f2 direct;
-        if (t == T - 1) {
-            direct = mul2(bc(C.gsn), one_minus_dist2(x));
-        } else {
-            const f2 om = (t == 0) ? om0 : om1;        // cached 1 - d^t
-            ga = fma2(mul2(gb, b[t]), om, ga);         // b^{t+1} = b^t a (1 - d^t)
-            direct = mul2(mul2(gb, a), om);
-        }
-        // the M-path is gated by [a != 0]
-        gb = fma2(mul2(mul2(uv, x), gate), bc(C.rS[t]), direct);
-        if (t == TT) {
-            x_tt = x;
-            uv_tt = uv;
-        }
-    }
-}
-
 // element offsets instead of six 64-bit pointers per capsule: the bases stay in the kernel-parameter bank
 // (offA and the in-block walker are 32-bit: qec_routing_fused_packed_supported bounds one bp block)
 struct Bwd2Geom {
@@ -810,6 +765,49 @@ __device__ __forceinline__ void bwd2_acc_sweep(int np, const Bwd2Geom& B, const 
     f2 an[3];  // two slots ahead: one was not enough under the prefetch traffic of the last sweep
     lda(0, an[0]);
     lda(1, an[1]);
+#if (QEC_SWP & 8)
+    Quat2 vn;
+    f2 o0n = bc(1.f), o1n = bc(1.f);
+    auto lds_slot = [&](int m) {
+        const int ps = threadIdx.x + m * kPT;
+        if (FULL || ps < np) {
+            vn = lds_pair(sA, sB, ps);
+            if (T >= 2) o0n = lds_f2(som0 + ps);
+            if (T >= 3) o1n = lds_f2(som1 + ps);
+        }
+    };
+    lds_slot(0);
+#pragma unroll
+    for (int m = 0; m < kPairs; ++m) {
+        if (m + 2 < kPairs) lda(m + 2, an[(m + 2) % 3]);
+        const int ps = threadIdx.x + m * kPT;
+        const Quat2 v = vn;
+        const f2 om0 = o0n, om1 = o1n;
+        if (m + 1 < kPairs) lds_slot(m + 1);  // ahead of this slot's red / cp.async (compiler barriers)
+        if (FULL || ps < np) {
+            const f2 a = an[m % 3];
+            const f2 gate = pk((lo(a) != 0.f) ? 1.f : 0.f, (hi(a) != 0.f) ? 1.f : 0.f);
+            f2 gb, ga, x, uv, b[kTB];
+            complete_levels2<T, TT>(C, v, a, gate, om0, om1, gb, ga, x, uv, b);
+            if (TT >= 1) {  // level TT-1: dL/dd_j = -g_b^TT b^{TT-1} a
+                const f2 xl = qdot2(C.ph[TT >= 1 ? TT - 1 : 0], v);
+                const f2 bl = b[TT >= 1 ? TT - 1 : 0];
+                const f2 gx = mul2(mul2(mul2(gb, bc(-1.f)), mul2(bl, a)), dist_grad2(xl));
+                a2[0] = fma2(gx, v.w, a2[0]); a2[1] = fma2(gx, v.x, a2[1]);
+                a2[2] = fma2(gx, v.y, a2[2]); a2[3] = fma2(gx, v.z, a2[3]);
+                acc_rank1_2(a2 + 4, bl, v);
+                sabs = (sabs + fabsf(lo(bl))) + fabsf(hi(bl));
+            }
+            if (TT == 0) {  // + dL/db^0 (b^0 = a)
+                const f2 g2 = add2(ga, gb);
+                asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(B.g_act + (size_t)B.offA + 2 * ps),
+                             "f"(lo(g2)), "f"(hi(g2))
+                             : "memory");
+            }
+        }
+        if (PREFETCH) prefetch_walk<FULL>(B, offT_next, wp, sA, sB, np, m);
+    }
+#else
 #pragma unroll
     for (int m = 0; m < kPairs; ++m) {
         if (m + 2 < kPairs) lda(m + 2, an[(m + 2) % 3]);
@@ -840,6 +838,7 @@ __device__ __forceinline__ void bwd2_acc_sweep(int np, const Bwd2Geom& B, const 
         }
         if (PREFETCH) prefetch_walk<FULL>(B, offT_next, wp, sA, sB, np, m);
     }
+#endif
 #pragma unroll
     for (int i = 0; i < 14; ++i) acc[i] = hsum(a2[i]);
     acc[14] = sabs;
@@ -864,9 +863,8 @@ __device__ __forceinline__ void bwd2_sweep0(int np, const Bwd2Geom& B, const Bwd
             a = ldg_f2(B.act + (size_t)B.offA + 2 * ps);
         }
     };
-    auto gen = [&](int m, const Quat2& lrf, f2 a) {
+    auto gen_t = [&](int m, const Quat2& lrf, f2 a, const Quat2& traw) {
         const int ps = threadIdx.x + m * kPT;
-        const Quat2 traw = lds_pair(sA, sB, ps);
         const Quat2 v = make_vote2<false>(lrf, traw).vote;
         sts_pair(sA, sB, ps, v);
         f2 b = a;
@@ -891,10 +889,23 @@ __device__ __forceinline__ void bwd2_sweep0(int np, const Bwd2Geom& B, const Bwd
     f2 av[3];
     ldl(0, lr[0], av[0]);
     ldl(1, lr[1], av[1]);
+#if (QEC_SWP & 16)
+    Quat2 tr[2];  // the transforms of slot M+1 leave shared memory before slot M is generated and stored
+    wait_slot<0>();
+    if (FULL || threadIdx.x < np) tr[0] = lds_pair(sA, sB, threadIdx.x);
+#define QEC_GEN_SLOT(M)                                                                              \
+    if ((M) + 2 < kPairs) ldl((M) + 2, lr[((M) + 2) % 3], av[((M) + 2) % 3]);                        \
+    if ((M) + 1 < kPairs) {                                                                          \
+        wait_slot<((M) + 1 < kPairs ? (M) + 1 : 0)>();                                               \
+        if (FULL || (threadIdx.x + ((M) + 1) * kPT < np)) tr[((M) + 1) & 1] = lds_pair(sA, sB, threadIdx.x + ((M) + 1) * kPT); \
+    }                                                                                                \
+    if (FULL || (threadIdx.x + (M) * kPT < np)) gen_t((M), lr[(M) % 3], av[(M) % 3], tr[(M) & 1]);
+#else
 #define QEC_GEN_SLOT(M)                                                       \
     if ((M) + 2 < kPairs) ldl((M) + 2, lr[((M) + 2) % 3], av[((M) + 2) % 3]); \
     wait_slot<(M)>();                                                         \
-    if (FULL || (threadIdx.x + (M) * kPT < np)) gen((M), lr[(M) % 3], av[(M) % 3]);
+    if (FULL || (threadIdx.x + (M) * kPT < np)) gen_t((M), lr[(M) % 3], av[(M) % 3], lds_pair(sA, sB, threadIdx.x + (M) * kPT));
+#endif
     QEC_GEN_SLOT(0) QEC_GEN_SLOT(1) QEC_GEN_SLOT(2) QEC_GEN_SLOT(3)
     QEC_GEN_SLOT(4) QEC_GEN_SLOT(5) QEC_GEN_SLOT(6) QEC_GEN_SLOT(7)
 #undef QEC_GEN_SLOT
@@ -954,20 +965,21 @@ __global__ void __launch_bounds__(kPT, kCtasPerSM)
         const int o = (int)(c - bp * O);
         return (size_t)bp * K * trow + (size_t)o * 4 * I;
     };
+    const long long BPn = Nc / O;
     if (cid < Nc) {
         OffWalk w = w0;
-        const size_t o0 = offT_of(cid);
+        const size_t o0 = offT_of(caps_of(cid, BPn, O));
 #pragma unroll
         for (int m = 0; m < kPairs; ++m) prefetch_walk<FULL>(B, o0, w, sA, sB, np, m);
     }
 
-    for (long long c = cid; c < Nc; c += ncl) {
+    for (long long u = cid; u < Nc; u += ncl) {
+        const long long c = caps_of(u, BPn, O);
         const long long bp = c / O;
         B.offA = (unsigned)bp * (unsigned)J + (unsigned)j_begin;
         B.offT = offT_of(c);
-        const long long cn = c + ncl;
-        const bool more = cn < Nc;
-        const size_t offT_next = more ? offT_of(cn) : (size_t)0;
+        const bool more = u + ncl < Nc;
+        const size_t offT_next = more ? offT_of(caps_of(u + ncl, BPn, O)) : (size_t)0;
         // Per-capsule state lives in memory between sweeps, not in registers: the poses are re-read from
         // poses_all (L2) and the adjoint vectors u^t / 1/S^t from a 32-float shared array, so that each
         // sweep only keeps what it uses live (the 28 registers of the full state made the sweeps spill).
@@ -1185,6 +1197,21 @@ extern "C" int qec_routing_fused_set_wide(int mode) {
     return g_wide_mode.load(std::memory_order_relaxed);
 }
 
+// Third generation (routing_fused3.cu: two capsules in flight per cluster, dedicated solver warp).  Bit 0: forward,
+// bit 1: backward.  Initial value from the environment (QEC_FUSED_PP, default 3 = both).
+extern "C" int qec_routing_fused_pp_supported(int K, int I, int O, int T);
+extern "C" int qec_routing_fused_pp_fwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
+                                        const float* beta, float* pose, float* agreement, float* poses_all, float* stats,
+                                        int BP, int K, int I, int O, int T, void* stream);
+static std::atomic<int> g_pp_mode{[] {
+    const char* e = getenv("QEC_FUSED_PP");
+    return (e != nullptr && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : QEC_PP_DEFAULT;
+}()};
+extern "C" int qec_routing_fused_set_pp(int mode) {
+    if (mode >= 0 && mode <= 3) return g_pp_mode.exchange(mode, std::memory_order_relaxed);
+    return g_pp_mode.load(std::memory_order_relaxed);
+}
+
 // 1 if the packed-pair kernels serve this geometry (callers normally just call qec_routing_fused_*,
 // which dispatch here when possible)
 extern "C" int qec_routing_fused_packed_supported(int K, int I, int O, int T) {
@@ -1206,6 +1233,9 @@ extern "C" int qec_routing_fused_fwd(const float* t_oqi, const float* lrfs, cons
     QEC_CHECK_ARG(act && alpha && beta, 3);
     QEC_CHECK_ARG(pose && agreement && poses_all && stats, 6);
     QEC_CHECK_ARG(BP > 0, 10);
+    if ((g_pp_mode.load(std::memory_order_relaxed) & 1) && qec_routing_fused_pp_supported(K, I, O, T))
+        return qec_routing_fused_pp_fwd(t_oqi, lrfs, act, alpha, beta, pose, agreement, poses_all, stats, BP, K, I, O, T,
+                                        stream);
     if (use_wide((long long)K * I, false))
         return qec_fused2_wide_fwd(t_oqi, lrfs, act, alpha, beta, pose, agreement, poses_all, stats, BP, K, I, O, T, stream);
     const int CL = pick_cluster(K * I);

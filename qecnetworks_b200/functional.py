@@ -129,6 +129,12 @@ def set_fused_wide(mode):
     return _lib.query("qec_routing_fused_set_wide", int(mode))
 
 
+def set_fused_pp(mode):
+    """bit 0: forward, bit 1: backward on the third-generation cluster kernels (qec_routing_fused_set_pp); returns
+    the previous mode"""
+    return _lib.query("qec_routing_fused_set_pp", int(mode))
+
+
 def routing_fused_forward_raw(t_oqi, lrfs, activation, alpha, beta, T):
     """no autograd: -> pose, agreement, poses_all [T,B,P,O,4], stats [B,P,O,2] (the last two are what
     the backward needs besides the inputs)"""
@@ -322,9 +328,11 @@ class RoutingSmall(torch.autograd.Function):
     beta only; the caller falls back to votes() + routing() when the inputs need gradients."""
 
     @staticmethod
-    def forward(ctx, xrot, lrfs, activation, Wc, bc, alpha, beta, num_iterations):
-        if any(ctx.needs_input_grad) and routing_small_supported(activation.shape[2], 1, bc.shape[0] // 4,
-                                                                 num_iterations) != 1:
+    def forward(ctx, xrot, lrfs, activation, Wc, bc, alpha, beta, num_iterations, keep):
+        # keep: a backward may follow (decided by the caller: inside forward() the grad mode is always off, and
+        # needs_input_grad reflects requires_grad of the inputs even under no_grad)
+        saved = bool(keep)
+        if saved and routing_small_supported(activation.shape[2], 1, bc.shape[0] // 4, num_iterations) != 1:
             raise _lib.QecLibraryError("routing_small: K > 16 is forward-only (inference); use votes() + routing()")
         B, P, K = activation.shape
         O = bc.shape[0] // 4
@@ -339,7 +347,7 @@ class RoutingSmall(torch.autograd.Function):
         dev = lrfs.device
         pose = torch.empty(B, P, O, 4, device=dev, dtype=torch.float32)
         agreement = torch.empty(B, P, O, device=dev, dtype=torch.float32)
-        saved = any(ctx.needs_input_grad)  # inference: nothing is kept for a backward (T x 16 B per capsule)
+        # inference: nothing is kept for a backward (T x 16 B per capsule)
         poses_all = torch.empty(T, B, P, O, 4, device=dev, dtype=torch.float32) if saved else None
         stats = torch.empty(B, P, O, 2, device=dev, dtype=torch.float32) if saved else None
         launch("qec_routing_small_fwd", xrot, lrfs, activation, Wc, bc, alpha, beta,
@@ -365,7 +373,7 @@ class RoutingSmall(torch.autograd.Function):
         launch("qec_routing_small_bwd", xrot, lrfs, activation, Wc, bc, alpha, beta,
              poses_all, stats, g_pose, g_agreement, g_Wc, g_bc, g_ab, B * P, K, O,
              ctx.T)
-        return None, None, None, g_Wc, g_bc, g_ab[0:1], g_ab[1:2], None
+        return None, None, None, g_Wc, g_bc, g_ab[0:1], g_ab[1:2], None, None
 
 
 def routing_small_supported(K, I, O, T):
@@ -374,7 +382,8 @@ def routing_small_supported(K, I, O, T):
 
 
 def routing_small(xrot, lrfs, activation, Wc, bc, alpha, beta, num_iterations):
-    return RoutingSmall.apply(xrot, lrfs, activation, Wc, bc, alpha, beta, num_iterations)
+    keep = torch.is_grad_enabled() and any(t.requires_grad for t in (Wc, bc, alpha, beta))
+    return RoutingSmall.apply(xrot, lrfs, activation, Wc, bc, alpha, beta, num_iterations, keep)
 
 
 def routing_fused_supported(K, I, O, T):

@@ -52,15 +52,6 @@ class _QecBase(torch.nn.Module):
     def pose_diff_loss(self, pose):
         return _pose_diff(pose)
 
-
-class QecNet(_QecBase):
-    def forward(self, points4pool1, lrfs4pool1, activation4pool1, pointspool1index=None):
-        return _two_pools(self, points4pool1, lrfs4pool1, activation4pool1)
-
-    def spread_loss(self, x, target, epoch=0):
-        return _spread(x, target.reshape(-1))
-
-
     def class_pose_loss(self, x, pose_out, target, pose_weight=0.1, margin=0.1):
         """The whole loss of train_cls_sia.py:70-79 in one launch: spread loss of the branch(es) + pose_weight x
         pose_diff_loss of the poses of the ground-truth class (the reference's per-sample selection loop
@@ -71,6 +62,14 @@ class QecNet(_QecBase):
         xs = x if x.dim() == 3 else x.unsqueeze(0)
         out = QF.class_pose_loss(xs, t.reshape(-1), pose_out, margin=margin, w_pose=pose_weight)
         return out[0], out[1].detach(), (pose_weight * out[2]).detach()
+
+
+class QecNet(_QecBase):
+    def forward(self, points4pool1, lrfs4pool1, activation4pool1, pointspool1index=None):
+        return _two_pools(self, points4pool1, lrfs4pool1, activation4pool1)
+
+    def spread_loss(self, x, target, epoch=0):
+        return _spread(x, target.reshape(-1))
 
 
 class QecSiaNet(_QecBase):

@@ -5,7 +5,9 @@ three rounds of (fused forward, pre-split fused backward); profile the third,
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from qecnetworks_b200 import functional as QF
+from qecnetworks_b200 import functional as QF, _lib
+if os.environ.get("QEC_LIB"):  # a variant built by scripts/build_variant.sh
+    _lib.LIB_PATH = os.path.abspath(os.environ["QEC_LIB"])
 
 B, P, K, I, O, T = 32, 1, 256, 128, 40, 3
 dev = torch.device("cuda:0")

@@ -44,3 +44,14 @@ with torch.no_grad():
         torch.cuda.synchronize()
         for (name, dims), ts in _lib.stop_kernel_timing().items():
             print("raw %s %.3f ms (min %.3f)" % (name, sum(ts) / len(ts), min(ts)))
+    # what the dL/dlrfs atomics (RED.ADD.F32x4 per vote, summed over the O capsules of a patch) cost: the same
+    # pre-split backward without that output
+    for _ in range(3):
+        QF.routing_fused_backward_raw(t_oqi, lrfs, act, alpha, beta, poses_all, stats, gp, ga, T, False, True, split=True)
+    torch.cuda.synchronize()
+    _lib.start_kernel_timing()
+    for _ in range(10):
+        QF.routing_fused_backward_raw(t_oqi, lrfs, act, alpha, beta, poses_all, stats, gp, ga, T, False, True, split=True)
+    torch.cuda.synchronize()
+    for (name, dims), ts in _lib.stop_kernel_timing().items():
+        print("raw-no-g_lrfs %s %.3f ms (min %.3f)" % (name, sum(ts) / len(ts), min(ts)))

@@ -3,6 +3,8 @@ import os, sys, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
 from qecnetworks_b200 import _lib
+if os.environ.get("QEC_LIB"):  # a variant built by scripts/build_variant.sh
+    _lib.LIB_PATH = os.path.abspath(os.environ["QEC_LIB"])
 sys.argv = [sys.argv[0]]
 exec(open(os.path.join(os.path.dirname(__file__), "xcheck_fused.py")).read().split("worst = 0.0")[0])
 BP, K, I, O, T = 32, 256, 128, 40, 3

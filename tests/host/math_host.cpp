@@ -59,6 +59,10 @@ void h_jacobi_full(int n, const float* M10, float* w, float* Vout) {
     }
 }
 
+void h_one_minus_dist_estrin(int n, const float* x, float* out) {
+    for (int i = 0; i < n; ++i) out[i] = one_minus_dist_estrin(x[i]);
+}
+
 void h_one_minus_dist(int n, const float* x, float* out, float* grad) {
     for (int i = 0; i < n; ++i) {
         out[i] = one_minus_dist(x[i]);

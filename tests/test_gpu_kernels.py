@@ -751,3 +751,49 @@ def test_routing_fused_uniform_random_votes_residual(K, I, O):
     assert float((lg - lam[..., 3]).abs().max()) < 1e-5
     if well.any():
         assert float(d[well].max()) < TOL
+
+
+# ---------------------------------------------------------------- third-generation cluster forward (opt-in)
+@pytest.mark.parametrize(
+    "B,P,K,I,O,T",
+    [
+        (2, 1, 32, 128, 5, 3),     # one CTA per capsule pair, every slot full, odd number of capsules per patch
+        (1, 1, 256, 128, 6, 3),    # J = 32768: clusters of 8, the geometry of pool2 at BASELINE config 2
+        (1, 2, 100, 30, 3, 2),     # ragged slice, T = 2
+        (2, 1, 37, 6, 5, 1),       # T = 1, tiny
+        (1, 1, 250, 100, 3, 3),    # J = 25000: ragged split over 8 CTAs
+    ],
+)
+def test_routing_fused_pp_forward(B, P, K, I, O, T):
+    """qec_routing_fused_pp_fwd (two capsules in flight per cluster, solver warps; csrc/routing_fused3.cu) against the
+    float64 oracle and against the second-generation kernel, and bit-reproducible run to run"""
+    from qecnetworks_b200 import functional as QF
+
+    dev = cuda()
+    from qecnetworks_b200 import _lib
+
+    assert _lib.query("qec_routing_fused_pp_supported", K, I, O, T) == 1
+    gen = torch.Generator().manual_seed(K * 5 + I)
+    J = K * I
+    lrfs = clustered((B, P, K, I), gen, spread=0.3)
+    act = (torch.rand(B, P, J, generator=gen) * 0.6 + 0.3) * (torch.rand(B, P, J, generator=gen) < 0.85)
+    act[:, :, 0] = 1.0
+    lrfs = lrfs * (act.view(B, P, K, I, 1) != 0)
+    base = torch.randn(1, 4, 1, O, generator=gen)
+    t_raw = (base + 0.25 * torch.randn(B * P * K, 4, I, O, generator=gen)).reshape(B * P * K, 4 * I * O)
+    alpha, beta = torch.tensor([1.2]), torch.tensor([0.8])
+    v = orc.votes_from(lrfs.double(), t_raw.double().view(B, P, K, 4, I, O))
+    pose_ref, agr_ref = orc.routing(v, act.double(), alpha.double(), beta.double(), T)
+    args = (t_raw[:, _oqi_perm(I, O)].contiguous().to(dev), lrfs.to(dev), act.to(dev), alpha.to(dev), beta.to(dev), T)
+    prev = QF.set_fused_pp(0)
+    try:
+        ref2 = QF.routing_fused_forward_raw(*args)
+        QF.set_fused_pp(1)
+        got = QF.routing_fused_forward_raw(*args)
+        again = QF.routing_fused_forward_raw(*args)
+    finally:
+        QF.set_fused_pp(prev)
+    assert quat_err(got[0].cpu(), pose_ref) < TOL and max_err(got[1].cpu(), agr_ref) < TOL
+    for a, b in zip(got, ref2):      # pose, agreement, poses_all, stats: the two generations agree to rounding
+        assert rel_err(a.cpu(), b.cpu()) < 2e-6
+    assert all(torch.equal(a, b) for a, b in zip(got, again))

@@ -513,5 +513,6 @@ def test_general_path_inference_is_sliced_over_the_batch():
         pose_a, agr_a = mod(pts, lr, ac)
         mod.INFERENCE_TEMP_BYTES = 32 * 3 * 5 * 4 * 6 * 5   # five samples per slice
         pose_b, agr_b = mod(pts, lr, ac)
-    assert torch.equal(pose_a, pose_b) and torch.equal(agr_a, agr_b)
+    # (not bit-identical: cuBLAS picks its tiling by the GEMM's row count, i.e. by the slice size)
+    assert quat_err(pose_a.cpu(), pose_b.cpu()) < 1e-5 and max_err(agr_a.cpu(), agr_b.cpu()) < 1e-5
     assert quat_err(pose_b[-2:].cpu(), g["pose"]) < TOL

@@ -118,6 +118,12 @@ def test_distance_polynomial(lib):
     # next to the clamp 1 - x^2 cancels: one float32 ulp of x is 3e-5 of the derivative
     assert (np.abs(grad - g) <= 2e-6 + 1e-4 * np.abs(g)).all()
     assert grad[np.abs(x) > np.float32(0.9999)].max() == 0.0 and grad[x == 0].max() == 0.0
+    # the Estrin form the cluster kernels evaluate (dependency depth 3 instead of 8): same accuracy
+    est = np.zeros_like(x)
+    lib.h_one_minus_dist_estrin(len(x), P(x), P(est))
+    d64 = 1 - 2 * np.arccos(np.minimum(np.abs(x.astype(np.float64)), np.float64(np.float32(0.9999)))) / np.pi
+    assert np.abs(est - d64).max() < 2e-7 and np.abs(out - d64).max() < 2e-7
+    assert np.abs(est - out).max() < 1.5e-7
 
 
 def test_top_eigenvector_adjoint(lib):
