@@ -19,7 +19,8 @@ constexpr int kLT = 128;
 template <int G>
 __global__ void __launch_bounds__(kLT)
     lrf_mean_fwd_kernel(const float* __restrict__ lrfs, const float* __restrict__ act, float* __restrict__ mean,
-                        long long Ncap, int K, int I) {
+                        long long Ncap, int K, int I, const float* __restrict__ points = nullptr,
+                        float* __restrict__ xrot = nullptr) {
     const long long gid = ((long long)blockIdx.x * kLT + threadIdx.x) / G;
     const bool active = gid < Ncap;
     const long long c = active ? gid : Ncap - 1;
@@ -39,6 +40,18 @@ __global__ void __launch_bounds__(kLT)
     Quat p = qfix(top_eigvec_psd(m, WarpDone()));  // (1/K) sum q q^T is positive semi-definite
     if (!(acc[10] > 0.f)) p = qmake(0.f, 0.f, 0.f, 0.f);
     if (active && coop.leader()) stq(mean + (size_t)c * 4, p);
+    // G = 1 (a handful of neighbours: the pool1 regime): the thread that owns the mean also rotates its K points,
+    // so the layer's prologue is one launch, not two (config 1 is latency: every launch is ~4 us of its ~20)
+    if (G == 1 && xrot != nullptr && active) {
+        const Quat cj = qconj(p);
+        for (int k = 0; k < K; ++k) {
+            const size_t bpk = (size_t)bp * K + k;
+            const float* pp = points + bpk * 3;
+            const Vec3 x = qrotv(cj, vmake(__ldg(pp), __ldg(pp + 1), __ldg(pp + 2)));
+            float* o = xrot + (bpk * I + i) * 3;
+            o[0] = x.x; o[1] = x.y; o[2] = x.z;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -243,9 +256,11 @@ extern "C" int qec_lrf_mean_fwd(const float* lrfs, const float* act, const float
     QEC_CHECK_ARG(I > 0, 8);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long Ncap = (long long)BP * I;
+    if (xrot != nullptr) QEC_CHECK_ARG(points, 3);
     if (K <= 32) {
         const long long blocks = (Ncap + kLT - 1) / kLT;
-        lrf_mean_fwd_kernel<1><<<(unsigned)blocks, kLT, 0, st>>>(lrfs, act, mean, Ncap, K, I);
+        lrf_mean_fwd_kernel<1><<<(unsigned)blocks, kLT, 0, st>>>(lrfs, act, mean, Ncap, K, I, points, xrot);
+        return launch_status();  // rotation done in the same launch
     } else if (I >= 32) {
         const long long blocks = (long long)BP * ((I + 31) / 32);
         lrf_mean_fwd_tile_kernel<<<(unsigned)blocks, kTW * 32, 0, st>>>(lrfs, act, mean, K, I);

@@ -74,6 +74,9 @@ namespace cg = cooperative_groups;
 #ifndef QEC_PP_DEFAULT
 #define QEC_PP_DEFAULT 0
 #endif
+#ifndef QEC_RED_SHFL
+#define QEC_RED_SHFL 0
+#endif
 __device__ __forceinline__ long long caps_of(long long u, long long BPn, int O) {
 #if QEC_SPREAD
     const long long o = u / BPn;
@@ -159,6 +162,32 @@ struct PushReducer {
         // phase n uses receive buffer / mbarrier n & 1.  A peer can be at most one phase ahead, so a
         // push of phase n + 1 never lands in the mbarrier that still collects phase n.
         const unsigned mb = mbar + 8u * (phase & 1u);
+#if QEC_RED_SHFL
+        // Variant: every warp folds its 32 lanes with a shuffle reduce-scatter BEFORE the CTA barrier (in the tail of
+        // its own sweep), so that after the barrier only 16 x kW floats are left to add: CL lanes per value read
+        // the kW warp sums in a fixed order and push.  Replaces 15 STS + 4 LDS.128 + 4 shuffles per thread.
+        {
+            constexpr int kW = NT / 32;
+            const int lane = tid & 31, warp = tid >> 5;
+            float w[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w[i] = (i < N) ? a[i] : 0.f;
+            const float mine = warp_reduce_scatter16(w, lane);
+            if ((lane & 1) == 0) scr[idx16(lane) * kW + warp] = mine;
+            if (tid == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(N * CL * 4) : "memory");
+            __syncthreads();
+            QEC_EVT(evt);
+            const int v = tid / CL, r = tid - v * CL;
+            if (v < N) {
+                float s = 0.f;
+#pragma unroll
+                for (int x = 0; x < kW; ++x) s += scr[v * kW + x];  // fixed order
+                const unsigned slot = smem_u32(buf + ((phase & 1u) * CL + rank) * 16 + v);
+                st_async_f32(mapa_u32(slot, r), s, mapa_u32(mb, r));
+            }
+        }
+#else
 #pragma unroll
         for (int i = 0; i < N; ++i) scr[i * NT + tid] = a[i];
         if (tid == 0)  // arm this phase: N floats from each of the CL CTAs
@@ -185,6 +214,7 @@ struct PushReducer {
             const unsigned slot = smem_u32(buf + ((phase & 1u) * CL + rank) * 16 + v);
             st_async_f32(mapa_u32(slot, part), s, mapa_u32(mb, part));
         }
+#endif
         QEC_EVT(evt + 1);
         if (tid < 32) {
             const unsigned parity = (phase >> 1) & 1u;

@@ -25,7 +25,8 @@
 
 namespace qec {
 
-constexpr int kST = 128;  // threads per CTA = output channels per CTA
+constexpr int kST = 128;  // threads per CTA = output channels per CTA (64 / 32 for layers with that few channels: the
+                          // stress sweep of BASELINE config 5 goes down to O = 32, where a 128-thread CTA idles 3 of 4 warps)
 
 template <int KMAX>
 struct PatchStage {  // per-patch inputs shared by all output channels
@@ -34,13 +35,13 @@ struct PatchStage {  // per-patch inputs shared by all output channels
     float a[KMAX];
 };
 
-template <int KMAX>
+template <int KMAX, int ST>
 __device__ __forceinline__ void stage_patch(PatchStage<KMAX>& s, const float* __restrict__ xrot,
                                             const float* __restrict__ lrfs, const float* __restrict__ act,
                                             long long bp, int K) {
     __syncthreads();  // previous patch fully consumed
-    const int k = threadIdx.x;
-    if (k < KMAX) {
+#pragma unroll
+    for (int k = threadIdx.x; k < KMAX; k += ST) {
         if (k < K) {
             const size_t e = (size_t)bp * K + k;
             s.x[k][0] = __ldg(xrot + e * 3);
@@ -79,8 +80,8 @@ struct ComposedRow {  // this thread's rows of Wc / bc: w[q][d], b[q]
 
 __device__ __forceinline__ Quat q_from(float4 v) { return qmake(v.x, v.y, v.z, v.w); }
 
-template <int KMAX>
-__global__ void __launch_bounds__(kST)
+template <int KMAX, int ST>
+__global__ void __launch_bounds__(ST)
     routing_small_fwd_kernel(const float* __restrict__ xrot, const float* __restrict__ lrfs,
                              const float* __restrict__ act, const float* __restrict__ Wc,
                              const float* __restrict__ bc, const float* __restrict__ alpha_p,
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(kST)
                              float* __restrict__ agreement, float* __restrict__ poses_all,
                              float* __restrict__ stats, int BP, int K, int O, int T) {
     __shared__ PatchStage<KMAX> st;
-    const int o_raw = blockIdx.y * kST + threadIdx.x;
+    const int o_raw = blockIdx.y * ST + threadIdx.x;
     const bool active = o_raw < O;
     const int o = active ? o_raw : O - 1;  // tail lanes shadow the last channel (warp-uniform solves)
     ComposedRow cr;
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(kST)
     const float alpha = __ldg(alpha_p), beta = __ldg(beta_p);
     const size_t Nc = (size_t)BP * O;
     for (long long bp = blockIdx.x; bp < BP; bp += gridDim.x) {
-        stage_patch(st, xrot, lrfs, act, bp, K);
+        stage_patch<KMAX, ST>(st, xrot, lrfs, act, bp, K);
         Quat v[KMAX];
         float b[KMAX];
         float acc[13];  // M (10), sum |b|, sum of vote components, sum b
@@ -157,8 +158,8 @@ __global__ void __launch_bounds__(kST)
 // vote tensor (34 GB at the largest corner of the sweep) or of t_raw exists.  Same results as the
 // register-resident kernel (same per-vote code, same accumulation order over k).
 // ------------------------------------------------------------------------------------
-template <int KMAX>
-__global__ void __launch_bounds__(kST)
+template <int KMAX, int ST>
+__global__ void __launch_bounds__(ST)
     routing_small_regen_fwd_kernel(const float* __restrict__ xrot, const float* __restrict__ lrfs,
                                    const float* __restrict__ act, const float* __restrict__ Wc,
                                    const float* __restrict__ bc, const float* __restrict__ alpha_p,
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(kST)
     __shared__ PatchStage<KMAX> st;
     extern __shared__ float sbw[];  // [K][kST] routing weights b^t of this thread's capsule
     float* bw = sbw + threadIdx.x;
-    const int o_raw = blockIdx.y * kST + threadIdx.x;
+    const int o_raw = blockIdx.y * ST + threadIdx.x;
     const bool active = o_raw < O;
     const int o = active ? o_raw : O - 1;
     ComposedRow cr;
@@ -176,14 +177,14 @@ __global__ void __launch_bounds__(kST)
     const float alpha = __ldg(alpha_p), beta = __ldg(beta_p);
     const size_t Nc = (size_t)BP * O;
     for (long long bp = blockIdx.x; bp < BP; bp += gridDim.x) {
-        stage_patch(st, xrot, lrfs, act, bp, K);
+        stage_patch<KMAX, ST>(st, xrot, lrfs, act, bp, K);
         float acc[13];
         zero_acc(acc);
 #pragma unroll 2
         for (int k = 0; k < K; ++k) {
             const Quat v = make_vote(q_from(st.lrf[k]), cr.apply(st.x[k])).vote;
             const float b = st.a[k];
-            bw[k * kST] = b;
+            bw[k * ST] = b;
             acc[10] += fabsf(b);
             acc[12] += b;
             acc_rank1(acc, b, v);
@@ -202,8 +203,8 @@ __global__ void __launch_bounds__(kST)
 #pragma unroll 2
             for (int k = 0; k < K; ++k) {
                 const Quat v = make_vote(q_from(st.lrf[k]), cr.apply(st.x[k])).vote;
-                const float b = bw[k * kST] * (st.a[k] * one_minus_dist(qdot(p, v)));
-                bw[k * kST] = b;
+                const float b = bw[k * ST] * (st.a[k] * one_minus_dist(qdot(p, v)));
+                bw[k * ST] = b;
                 acc[10] += fabsf(b);
                 acc[12] += b;
                 acc_rank1(acc, b, v);
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(kST)
 #pragma unroll 2
         for (int k = 0; k < K; ++k) {
             const Quat v = make_vote(q_from(st.lrf[k]), cr.apply(st.x[k])).vote;
-            const float b = bw[k * kST];
+            const float b = bw[k * ST];
             ssum = fmaf(b, one_minus_dist(qdot(p, v)), ssum);
             n += (b != 0.f) ? 1.f : 0.f;
         }
@@ -231,8 +232,8 @@ __global__ void __launch_bounds__(kST)
 
 // backward for the case where only the parameters need gradients (pool1: the LRFs, points and
 // 0/1 activations are data): dL/dWc [4O,3], dL/dbc [4O], dL/dalpha, dL/dbeta, all ACCUMULATED.
-template <int KMAX>
-__global__ void __launch_bounds__(kST, 4)
+template <int KMAX, int ST>
+__global__ void __launch_bounds__(ST, 512 / ST)
     routing_small_bwd_kernel(const float* __restrict__ xrot, const float* __restrict__ lrfs,
                              const float* __restrict__ act, const float* __restrict__ Wc,
                              const float* __restrict__ bc, const float* __restrict__ alpha_p,
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(kST, 4)
                              const float* __restrict__ g_agr, float* g_Wc, float* g_bc, float* g_alpha_beta, int BP,
                              int K, int O, int T) {
     __shared__ PatchStage<KMAX> st;
-    const int o_raw = blockIdx.y * kST + threadIdx.x;
+    const int o_raw = blockIdx.y * ST + threadIdx.x;
     const bool active = o_raw < O;
     const int o = active ? o_raw : O - 1;
     ComposedRow cr;
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(kST, 4)
     }
     float ga_tot = 0.f, gb_tot = 0.f;
     for (long long bp = blockIdx.x; bp < BP; bp += gridDim.x) {
-        stage_patch(st, xrot, lrfs, act, bp, K);
+        stage_patch<KMAX, ST>(st, xrot, lrfs, act, bp, K);
         const size_t c = (size_t)bp * O + o;
         const float s = __ldg(stats + 2 * c), n = __ldg(stats + 2 * c + 1);
         const bool has = n > 0.f;
@@ -343,21 +344,53 @@ __global__ void __launch_bounds__(kST, 4)
 }
 
 static int small_kmax(int K) { return K <= 9 ? 9 : (K <= 16 ? 16 : 0); }
+static int small_threads(int O) { return O <= 32 ? 32 : (O <= 64 ? 64 : kST); }
 
-// persistent grid: exactly as many CTAs as are co-resident (one wave), each walking over many patches
+// persistent grid: exactly as many CTAs as are co-resident (one wave), each walking over many patches.
+// `cache`: CTAs per SM of this kernel instantiation, per device.
 template <class Kern>
-static dim3 small_grid(Kern kern, int BP, int O, PerDeviceInt& cache) {
-    const int gy = (O + kST - 1) / kST;
+static dim3 small_grid(Kern kern, int threads, size_t smem, int BP, int O, PerDeviceInt& cache) {
+    const int gy = (O + threads - 1) / threads;
     std::atomic<int>* slot = cache.slot();
     int per_sm = slot ? slot->load(std::memory_order_relaxed) : -1;
     if (per_sm < 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kST, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1)
+            per_sm = 4;
         if (slot) slot->store(per_sm, std::memory_order_relaxed);
     }
     int gx = (kNumSMs * per_sm) / gy;
     if (gx < 1) gx = 1;
     if (gx > BP) gx = BP;
     return dim3((unsigned)gx, (unsigned)gy);
+}
+
+template <int KMAX, int ST>
+static void launch_small_fwd(const float* xrot, const float* lrfs, const float* act, const float* Wc, const float* bc,
+                             const float* alpha, const float* beta, float* pose, float* agreement, float* poses_all,
+                             float* stats, int BP, int K, int O, int T, cudaStream_t st) {
+    static PerDeviceInt occ;
+    const dim3 grid = small_grid(routing_small_fwd_kernel<KMAX, ST>, ST, 0, BP, O, occ);
+    routing_small_fwd_kernel<KMAX, ST><<<grid, ST, 0, st>>>(xrot, lrfs, act, Wc, bc, alpha, beta, pose, agreement,
+                                                            poses_all, stats, BP, K, O, T);
+}
+template <int ST>
+static void launch_small_regen_fwd(const float* xrot, const float* lrfs, const float* act, const float* Wc,
+                                   const float* bc, const float* alpha, const float* beta, float* pose, float* agreement,
+                                   float* poses_all, float* stats, int BP, int K, int O, int T, cudaStream_t st) {
+    static PerDeviceInt occ;  // sized for the largest K, so one cached value serves every K
+    const dim3 grid = small_grid(routing_small_regen_fwd_kernel<64, ST>, ST, 64 * ST * sizeof(float), BP, O, occ);
+    routing_small_regen_fwd_kernel<64, ST><<<grid, ST, (size_t)K * ST * sizeof(float), st>>>(
+        xrot, lrfs, act, Wc, bc, alpha, beta, pose, agreement, poses_all, stats, BP, K, O, T);
+}
+template <int KMAX, int ST>
+static void launch_small_bwd(const float* xrot, const float* lrfs, const float* act, const float* Wc, const float* bc,
+                             const float* alpha, const float* beta, const float* poses_all, const float* stats,
+                             const float* g_pose, const float* g_agreement, float* g_Wc, float* g_bc, float* g_ab, int BP,
+                             int K, int O, int T, cudaStream_t st) {
+    static PerDeviceInt occ;
+    const dim3 grid = small_grid(routing_small_bwd_kernel<KMAX, ST>, ST, 0, BP, O, occ);
+    routing_small_bwd_kernel<KMAX, ST><<<grid, ST, 0, st>>>(xrot, lrfs, act, Wc, bc, alpha, beta, poses_all, stats, g_pose,
+                                                            g_agreement, g_Wc, g_bc, g_ab, BP, K, O, T);
 }
 
 }  // namespace qec
@@ -383,34 +416,13 @@ extern "C" int qec_routing_small_fwd(const float* xrot, const float* lrfs, const
     QEC_CHECK_ARG(BP > 0, 12);
     QEC_CHECK_ARG(qec_routing_small_supported(K, 1, O, T), 13);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (small_kmax(K) == 0) {  // 16 < K <= 64: votes regenerated per sweep, weights in (dynamic) shared memory
-        static PerDeviceInt occr;
-        const size_t smem = (size_t)K * kST * sizeof(float);
-        const int gy = (O + kST - 1) / kST;
-        std::atomic<int>* slot = occr.slot();
-        int per_sm = slot ? slot->load(std::memory_order_relaxed) : -1;
-        if (per_sm < 0) {  // sized for the largest K, so one cached value serves every K
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, routing_small_regen_fwd_kernel<64>, kST,
-                                                              64 * kST * sizeof(float)) != cudaSuccess || per_sm < 1)
-                per_sm = 4;
-            if (slot) slot->store(per_sm, std::memory_order_relaxed);
-        }
-        int gx = (kNumSMs * per_sm) / gy;
-        if (gx < 1) gx = 1;
-        if (gx > BP) gx = BP;
-        routing_small_regen_fwd_kernel<64><<<dim3((unsigned)gx, (unsigned)gy), kST, smem, st>>>(
-            xrot, lrfs, act, Wc, bc, alpha, beta, pose, agreement, poses_all, stats, BP, K, O, T);
-        return launch_status();
-    }
-    static PerDeviceInt occ9, occ16;
-    const dim3 grid = (small_kmax(K) == 9) ? small_grid(routing_small_fwd_kernel<9>, BP, O, occ9)
-                                           : small_grid(routing_small_fwd_kernel<16>, BP, O, occ16);
-    if (small_kmax(K) == 9)
-        routing_small_fwd_kernel<9><<<grid, kST, 0, st>>>(xrot, lrfs, act, Wc, bc, alpha, beta, pose, agreement,
-                                                          poses_all, stats, BP, K, O, T);
-    else
-        routing_small_fwd_kernel<16><<<grid, kST, 0, st>>>(xrot, lrfs, act, Wc, bc, alpha, beta, pose, agreement,
-                                                           poses_all, stats, BP, K, O, T);
+    const int km = small_kmax(K), th = small_threads(O);
+#define QEC_SMALL_FWD(ST_)                                                                                              \
+    if (km == 0) launch_small_regen_fwd<ST_>(xrot, lrfs, act, Wc, bc, alpha, beta, pose, agreement, poses_all, stats, BP, K, O, T, st); \
+    else if (km == 9) launch_small_fwd<9, ST_>(xrot, lrfs, act, Wc, bc, alpha, beta, pose, agreement, poses_all, stats, BP, K, O, T, st); \
+    else launch_small_fwd<16, ST_>(xrot, lrfs, act, Wc, bc, alpha, beta, pose, agreement, poses_all, stats, BP, K, O, T, st);
+    if (th == 32) { QEC_SMALL_FWD(32) } else if (th == 64) { QEC_SMALL_FWD(64) } else { QEC_SMALL_FWD(128) }
+#undef QEC_SMALL_FWD
     return launch_status();
 }
 
@@ -427,14 +439,11 @@ extern "C" int qec_routing_small_bwd(const float* xrot, const float* lrfs, const
     QEC_CHECK_ARG(BP > 0, 15);
     QEC_CHECK_ARG(qec_routing_small_supported(K, 1, O, T) == 1, 16);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    static PerDeviceInt occ9, occ16;
-    const dim3 grid = (small_kmax(K) == 9) ? small_grid(routing_small_bwd_kernel<9>, BP, O, occ9)
-                                           : small_grid(routing_small_bwd_kernel<16>, BP, O, occ16);
-    if (small_kmax(K) == 9)
-        routing_small_bwd_kernel<9><<<grid, kST, 0, st>>>(xrot, lrfs, act, Wc, bc, alpha, beta, poses_all, stats,
-                                                          g_pose, g_agreement, g_Wc, g_bc, g_alpha_beta, BP, K, O, T);
-    else
-        routing_small_bwd_kernel<16><<<grid, kST, 0, st>>>(xrot, lrfs, act, Wc, bc, alpha, beta, poses_all, stats,
-                                                           g_pose, g_agreement, g_Wc, g_bc, g_alpha_beta, BP, K, O, T);
+    const int km = small_kmax(K), th = small_threads(O);
+#define QEC_SMALL_BWD(ST_)                                                                                             \
+    if (km == 9) launch_small_bwd<9, ST_>(xrot, lrfs, act, Wc, bc, alpha, beta, poses_all, stats, g_pose, g_agreement, g_Wc, g_bc, g_alpha_beta, BP, K, O, T, st); \
+    else launch_small_bwd<16, ST_>(xrot, lrfs, act, Wc, bc, alpha, beta, poses_all, stats, g_pose, g_agreement, g_Wc, g_bc, g_alpha_beta, BP, K, O, T, st);
+    if (th == 32) { QEC_SMALL_BWD(32) } else if (th == 64) { QEC_SMALL_BWD(64) } else { QEC_SMALL_BWD(128) }
+#undef QEC_SMALL_BWD
     return launch_status();
 }

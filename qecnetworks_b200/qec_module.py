@@ -264,7 +264,18 @@ class QecModule(Module):
             # register-resident kernel evaluate Wc x + bc per vote -- no [B*P*K, 4*O] tensor, no GEMM
             W1, b1 = self.quater_gen1.weight, self.quater_gen1.bias
             W2, b2 = self.quater_gen2.weight, self.quater_gen2.bias
-            Wc, bc = _ComposeFP32.apply(W1, b1, W2, b2)
+            if param_grad:
+                Wc, bc = _ComposeFP32.apply(W1, b1, W2, b2)
+            else:
+                # inference: the composition depends on the parameters only -- keep it until one of them changes
+                # (tensor version counters / storage), two launches less per forward
+                key = tuple((t.data_ptr(), t._version, t.device) for t in (W1, b1, W2, b2))
+                cached = getattr(self, "_composed", None)
+                if cached is None or cached[0] != key:
+                    with torch.no_grad():
+                        cached = (key, _ComposeFP32.apply(W1, b1, W2, b2))
+                    self._composed = cached
+                Wc, bc = cached[1]
             pose, agreement = QF.routing_small(xrot, lrfs, act_flat, Wc, bc, self.alpha, self.beta,
                                                self.num_iterations)
             return pose.squeeze(-2), agreement
