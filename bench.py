@@ -288,6 +288,11 @@ def kernel_work(name, dims, T):
                     32 * Nn + (16 * T + 28) * Nc)
         return (32 * Nv + 4 * Nn + 20 * Nc, (2 * (24 + 48) + 49 * (T + 1)) * Nv + 300 * Nc,
                 32 * Nn + (16 * T + 28) * Nc)
+    if name == "qec_gen2_bwd":
+        # backward of quater_gen2 (two products over the transform gradient g [M, N], both outputs tiny): the
+        # algorithmic minimum reads g once; this implementation reads it once per product (tcgen05 tf32 x3, TMA-fed)
+        M, N, Kc = dims[:3]
+        return 4 * M * N + 8 * (M + N) * Kc, 2 * 2 * M * N * (Kc + 1), 8 * M * N + 2 * 24 * 48 * 4 * (M + N)
     if name in ("qec_lrf_mean_fwd", "qec_lrf_mean_bwd"):
         BP, K, I = dims[:3]
         Nn, Nm = BP * K * I, BP * I

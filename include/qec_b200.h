@@ -190,6 +190,19 @@ int qec_split_operand(const float* src, const float* extra, float extra_const, c
 int qec_fold_chunks(const float* a, const float* b, const long long* perm, float* out_main, float* out_last, int S,
                     long long R, int KP, int K, int ld_main, void* stream);
 
+/* Backward of the transform generator quater_gen2 = nn.Linear(O, 4*I*O) of the pool2 layer
+ * (models/qec_module.py:124 and its autograd) on the tcgen05 tensor cores at FP32 accuracy (3-term TF32 split,
+ * accumulator in tensor memory; csrc/gen2_bwd.cu):
+ *   g [M, N] = dL/dt (FP32, as qec_routing_fused_bwd writes it; M = B*P*K, N = 4*I*O in capsule-major column order),
+ *   h [M, Kc] = the layer's input, W2 [N, Kc] = its weight in the reference's row order, perm [N] int64 = the row of
+ *   W2 behind column n of g  ->  g_h [M, Kc] = g Wp (NULL to skip), g_W2 [N, Kc] and g_b2 [N] (both or neither).
+ * workspace: qec_gen2_bwd_workspace(M, N, Kc) floats.  Supported: M, N multiples of 128, Kc <= 47
+ * (qec_gen2_bwd_supported).  variant: 0 (other values select descriptor-stride conventions; bring-up aid). */
+int qec_gen2_bwd_supported(int M, int N, int Kc);
+long long qec_gen2_bwd_workspace(int M, int N, int Kc);
+int qec_gen2_bwd(const float* g, const float* h, const float* W2, const long long* perm, float* g_h, float* g_W2,
+                 float* g_b2, float* workspace, int M, int N, int Kc, int variant, void* stream);
+
 /* Spread loss of QEC-Net and its gradient in one launch pair (reference models/qec_net.py:53-59,
  * margin 0.1): loss [1] = mean_b sum_{c != y_b} relu(m - (x[b,y_b] - x[b,c]))^2, g_x [B, C] = dloss/dx.
  * scratch: B floats.  err: device int set to 1 if a label is outside [0, C) (the reference's

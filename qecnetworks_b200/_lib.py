@@ -45,6 +45,9 @@ SIGNATURES = {
     "qec_knn": ([_P] * 5 + [_I, _I, _I, _I, _P], 1),
     "qec_split_operand": ([_P, _P, _F, _P, _P, _P, _LL, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], 1),
     "qec_fold_chunks": ([_P, _P, _P, _P, _P, _I, _LL, _I, _I, _I, _P], 1),
+    "qec_gen2_bwd_supported": ([_I, _I, _I], 0),
+    "qec_gen2_bwd_workspace": ([_I, _I, _I], 0),
+    "qec_gen2_bwd": ([_P] * 8 + [_I, _I, _I, _I, _P], lambda a: 2 + (1 if a[4] else 0) + (1 if a[5] else 0)),
     "qec_spread_loss": ([_P, _P, _F, _P, _P, _P, _P, _I, _I, _P], 2),
     "qec_class_pose_loss": ([_P, _P, _F, _P, _F, _P, _P, _P, _P, _I, _I, _I, _P], 1),
     "qec_quat_eval": ([_P, _P, _P, _P, _LL, _P], 1),
@@ -79,7 +82,7 @@ def load():
             for name, (argtypes, _) in SIGNATURES.items():
                 fn = getattr(lib, name)
                 fn.argtypes = argtypes
-                fn.restype = ctypes.c_int
+                fn.restype = ctypes.c_longlong if name.endswith("_workspace") else ctypes.c_int
             _lib = lib
     return _lib
 

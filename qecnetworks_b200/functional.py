@@ -263,6 +263,30 @@ def spread_loss(x, target, margin=0.1):
     return SpreadLoss.apply(x, target, margin)
 
 
+def gen2_bwd_supported(M, N, Kc):
+    return bool(_lib.query("qec_gen2_bwd_supported", int(M), int(N), int(Kc)))
+
+
+def gen2_backward(g, h, W2, perm, need_h=True, need_w=True):
+    """Backward of quater_gen2 (reference qec_module.py:124) from the FP32 transform gradient g [M, N] on the tcgen05
+    tensor cores (qec_gen2_bwd: TMA-fed, 3-term TF32 split, accumulator in tensor memory):
+    -> (g_h [M, Kc] | None, g_W2 [N, Kc] | None, g_b2 [N] | None)"""
+    M, N = g.shape
+    Kc = h.shape[1]
+    g = _check(g, "g", (M, N))
+    h = _check(h, "h", (M, Kc))
+    W2 = _check(W2, "W2", (N, Kc))
+    if perm.dtype != torch.int64 or not perm.is_cuda:
+        raise TypeError("perm must be a CUDA int64 tensor")
+    dev = g.device
+    ws = torch.empty(int(_lib.query("qec_gen2_bwd_workspace", M, N, Kc)), device=dev, dtype=torch.float32)
+    g_h = torch.empty(M, Kc, device=dev, dtype=torch.float32) if need_h else None
+    g_W2 = torch.empty(N, Kc, device=dev, dtype=torch.float32) if need_w else None
+    g_b2 = torch.empty(N, device=dev, dtype=torch.float32) if need_w else None
+    launch("qec_gen2_bwd", g, h, W2, perm.contiguous(), g_h, g_W2, g_b2, ws, M, N, Kc, 0)
+    return g_h, g_W2, g_b2
+
+
 class ClassPoseLoss(torch.autograd.Function):
     """(x [S,B,C] | None, labels [B], pose [2,B,C,4] | None) -> loss [3] = {total, spread, pose_diff}: the spread
     loss of S branches (reference qec_net.py:53-59 / qec_sia_net.py:69-77) + w_pose x the pose-difference loss on

@@ -117,6 +117,12 @@ class _SplitTf32Matmul(torch.autograd.Function):
         return g_xa, g_wa
 
 
+# Backward of quater_gen2 on the package's own tcgen05 kernel (1) or on cuBLAS over the pre-split gradient (0).
+import os as _os
+
+GEN2_BACKWARD_TCGEN05 = _os.environ.get("QEC_GEN2_TC", "1") != "0"
+
+
 def _chunks(n, length=1024):
     """number of chunks (a power of two dividing n) that makes them about `length` long"""
     s = 1
@@ -159,6 +165,15 @@ class _TransformRoutingFused(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_pose, g_agreement):
         h, W2, b2, perm, t_oqi, lrfs, activation, alpha, beta, poses_all, stats = ctx.saved_tensors
+        need_h, need_w = ctx.needs_input_grad[0], (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        if GEN2_BACKWARD_TCGEN05 and QF.gen2_bwd_supported(t_oqi.shape[0], t_oqi.shape[1], h.shape[1]):
+            # the transform gradient leaves the routing backward as plain FP32 and both products of the Linear's
+            # backward run on this package's own tcgen05 kernel (csrc/gen2_bwd.cu) instead of four cuBLAS bmm's
+            g_t, g_lrfs, g_act, g_ab = QF.routing_fused_backward_raw(
+                t_oqi, lrfs, activation, alpha, beta, poses_all, stats, g_pose, g_agreement, ctx.T,
+                ctx.needs_input_grad[4], ctx.needs_input_grad[5], split=False)
+            g_h, g_W2, g_b2 = QF.gen2_backward(g_t, h, W2, perm, need_h, need_w)
+            return g_h, g_W2, g_b2, None, g_lrfs, g_act, g_ab[0:1], g_ab[1:2], None
         (g_hi, g_lo), g_lrfs, g_act, g_ab = QF.routing_fused_backward_raw(
             t_oqi, lrfs, activation, alpha, beta, poses_all, stats, g_pose, g_agreement, ctx.T,
             ctx.needs_input_grad[4], ctx.needs_input_grad[5], split=True)

@@ -465,12 +465,15 @@ def test_routing_fused_packed_vs_scalar_and_split(B, P, K, I, O, T, wide, fused_
     assert bool(((hi + lo - g).abs() <= g.abs() * 2.0 ** -19 + 1e-37).all())   # BF16 remainder: ~2^-20 |g| left
 
 
-def test_transform_routing_node_matches_plain_path():
-    """_TransformRoutingFused (tensor-core backward GEMMs fed by the pre-split gradient) against the plain
-    path (FP32 SGEMM backward) on a pool2-shaped layer: same outputs, same gradients"""
+@pytest.mark.parametrize("tcgen05", [True, False])
+def test_transform_routing_node_matches_plain_path(tcgen05, monkeypatch):
+    """_TransformRoutingFused -- backward of quater_gen2 on the package's tcgen05 kernel (qec_gen2_bwd) or on cuBLAS
+    over the pre-split gradient -- against the plain path (FP32 SGEMM backward) on a pool2-shaped layer: same
+    outputs, same gradients"""
     from qecnetworks_b200 import functional as QF
     from qecnetworks_b200 import qec_module as QM
 
+    monkeypatch.setattr(QM, "GEN2_BACKWARD_TCGEN05", tcgen05)
     dev = cuda()
     B, P, K, I, O, T = 2, 1, 256, 128, 5, 3
     gen = torch.Generator().manual_seed(5)
@@ -797,3 +800,35 @@ def test_routing_fused_pp_forward(B, P, K, I, O, T):
     for a, b in zip(got, ref2):      # pose, agreement, poses_all, stats: the two generations agree to rounding
         assert rel_err(a.cpu(), b.cpu()) < 2e-6
     assert all(torch.equal(a, b) for a, b in zip(got, again))
+
+
+# ---------------------------------------------------------------- tcgen05 backward of quater_gen2
+@pytest.mark.parametrize("M,N,Kc", [(128, 128, 40), (256, 384, 7), (512, 20480, 40), (2048, 5120, 47)])
+def test_gen2_backward_tcgen05(M, N, Kc):
+    """qec_gen2_bwd (TMA + tcgen05 tf32 x3, accumulator in tensor memory; csrc/gen2_bwd.cu) against float64 matmuls:
+    dL/dh = g Wp, dL/dW2 = (g^T h) scattered through the row permutation, dL/db2 = column sums of g -- the backward of
+    the reference's quater_gen2 = nn.Linear(O, 4*I*O) (qec_module.py:124), within 2e-5 of the largest entry"""
+    from qecnetworks_b200 import functional as QF
+
+    dev = cuda()
+    assert QF.gen2_bwd_supported(M, N, Kc)
+    gen = torch.Generator().manual_seed(M + N + Kc)
+    g = torch.randn(M, N, generator=gen).to(dev) * torch.rand(M, 1, generator=gen).to(dev)
+    h = torch.randn(M, Kc, generator=gen).to(dev)
+    W2 = (torch.randn(N, Kc, generator=gen) / 6).to(dev)
+    perm = torch.randperm(N, generator=gen).to(dev)
+    g_h, g_W2, g_b2 = QF.gen2_backward(g, h, W2, perm)
+    ref_h = g.double() @ W2.double()[perm]
+    ref_w = torch.empty(N, Kc, device=dev, dtype=torch.float64)
+    ref_w[perm] = g.double().t() @ h.double()
+    ref_b = torch.empty(N, device=dev, dtype=torch.float64)
+    ref_b[perm] = g.double().sum(0)
+    for got, ref, name in ((g_h, ref_h, "dh"), (g_W2, ref_w, "dW2"), (g_b2, ref_b, "db2")):
+        e = rel_err(got.cpu(), ref.cpu())
+        print("gen2 margin %s M=%d N=%d err=%.2e tol=2e-5" % (name, M, N, e))
+        assert e < 2e-5, (name, e)
+    only_h = QF.gen2_backward(g, h, W2, perm, need_w=False)
+    assert only_h[1] is None and torch.equal(only_h[0], g_h)
+    again = QF.gen2_backward(g, h, W2, perm)
+    assert all(torch.equal(a, b) for a, b in zip(again, (g_h, g_W2, g_b2)))   # no atomics: bit-reproducible
+    assert not QF.gen2_bwd_supported(100, 128, 40) and not QF.gen2_bwd_supported(128, 128, 48)

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import qec_oracle as orc
-from tests.util import load_golden, params_of, quat_err, max_err, rel_err, grads_close
+from tests.util import load_golden, params_of, quat_err, max_err, rel_err, grads_close, sum_of_terms_scale
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -280,6 +280,7 @@ def test_sia_net_vs_oracle_full_geometry():
     p2, l2, a2, labels = _sia_inputs(2, 40, seed=41)
     p64 = {k: v.double().requires_grad_(True) for k, v in params.items()}
     pose_ref, a_ref = orc.qec_sia_net_forward(p64, p2.double(), l2.double(), a2.double(), 3)
+    a_ref.retain_grad()
     cls_ref = orc.sia_spread_loss(a_ref, labels)
     sel = torch.stack([pose_ref[:, i, labels[i]] for i in range(2)], 1)   # train_cls_sia.py:76-77
     pose_loss_ref = 0.1 * orc.pose_diff_loss(sel)
@@ -300,7 +301,9 @@ def test_sia_net_vs_oracle_full_geometry():
     assert abs(float(alt) - float(total)) < 1e-6
     total.backward()
     got = {k: v.grad.cpu() for k, v in net.named_parameters()}
-    assert grads_close(got, {k: p64[k].grad for k in got}, TOL) == []
+    # d loss / d pool2.beta = sum over the 160 output capsules of terms that cancel to ~1e-2 of their magnitudes
+    assert grads_close(got, {k: p64[k].grad for k in got}, TOL,
+                       term_scales={"pool2.beta": sum_of_terms_scale(a_ref, a_ref.grad)}) == []
 
 
 def test_sia_full_size_properties_and_rotation_error():

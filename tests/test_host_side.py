@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     src = open(os.path.join(ROOT, "include", "qec_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return re.findall(r"\bint\s+(qec_\w+)\s*\(", src)
+    return re.findall(r"\b(?:int|long long)\s+(qec_\w+)\s*\(", src)
 
 
 def test_library_exports_every_declared_symbol():
@@ -37,7 +37,8 @@ def test_library_exports_every_declared_symbol():
 
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
     exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln and ln.split()[-1].startswith("qec_")}
-    assert exported <= set(names) | {"qec_prof_read"}, exported - set(names)  # (qec_prof_read: -DQEC_PROF builds only)
+    # (qec_prof_read / qec_prof3_read: -DQEC_PROF builds only)
+    assert exported <= set(names) | {"qec_prof_read", "qec_prof3_read"}, exported - set(names)
 
 
 def test_argument_validation_without_gpu():
