@@ -13,22 +13,24 @@
 //   mode 0 (dh): CTA = 128 rows of g x a slice of the columns; chunk = [128 x 32]; A is K-major (k = column).
 //   mode 1 (dW): CTA = 128 columns of g x a slice of the rows;  chunk = [32 x 128]; A is MN-major (k = row): the
 //                tensor core reads g^T straight from the same kind of tile -- no transposed copy of g anywhere.
-// Shared-memory tiles use the swizzle-free UMMA "interleaved" layout of 8-row x 16-byte core matrices.  For a
-// row-major FP32 tile a core matrix holds 8 rows x 4 consecutive columns either way, so ONE tile format, filled by
-// 16-byte cp.async (8 rows x 64 contiguous bytes per warp instruction: full sectors from global, conflict-free in
-// shared memory), serves as K-major operand (k along the columns) and as MN-major operand (k along the rows); only
-// the two descriptor strides swap.
+// Shared-memory tiles are written by TMA in the tensor core's canonical swizzled layouts: 128-byte swizzle for the
+// K-major operands (rows of 128 B = 32 k), and -- for g^T -- the 128-byte swizzle with a 32-byte base, which is the
+// one MN-major layout tcgen05 accepts for 32-bit operands (the swizzle-free "interleaved" MN-major form computes
+// zeros for tf32: measured).
 //
 // FP32 accuracy: tf32 keeps 10 mantissa bits, so every operand is split x = hi + lo with hi on the TF32 grid and
-//   A B = A_hi B_hi + A_hi B_lo + A_lo B_hi      (the dropped lo*lo term is 2^-22 relative)
-// accumulated in FP32 in tensor memory.  The small operands are split once by a prep kernel; the tile of g is split
-// in shared memory by the threads that loaded it (hi overwrites the tile, lo goes to a twin tile), so nothing
-// depends on how the hardware would round an FP32 input.
+//   A B = A_hi [B_hi | B_lo] + A_lo B_hi         (the dropped lo*lo term is 2^-22 relative)
+// accumulated in FP32 in tensor memory (96 columns: the hi*lo products keep an accumulator of their own and are added
+// in the epilogue).  The small operands are split once by a prep kernel (hi rounded to the TF32
+// grid); for the tile of g, hi is what the tensor core itself reads from an FP32 word -- the upper 19 bits, i.e.
+// truncation, verified bit-for-bit against an explicitly masked copy -- and lo = x - trunc(x) is written to a twin
+// tile by four splitter warps.
 //
-// Warp roles (160 threads): warps 0-3 load (cp.async ring of kStages chunks), split, and finally drain the accumulator
-// (tcgen05.ld) to a partial-sum buffer; warp 4 allocates tensor memory and one of its lanes issues the MMAs.
-// full[s] / empty[s] mbarriers hand chunks between them (tcgen05.commit arrives on empty[s] when the MMAs that read
-// stage s have finished).  A small fold kernel adds the partial sums of the column / row slices in a fixed order and
+// Warp roles (192 threads): warp 5 = TMA producer (cp.async.bulk.tensor into a ring of kStages stages, completion
+// on an mbarrier), warps 0-3 = splitters and finally the epilogue (tcgen05.ld of the accumulator to a partial-sum
+// buffer), warp 4 allocates tensor memory and one of its lanes issues the MMAs; tcgen05.commit returns a stage to the
+// producer when the MMAs that read it have finished.  (A first version fed the ring with 16-byte cp.async from 128
+// threads: 731 us for both products; TMA: 405 us -- the SM could not keep enough 16-byte requests in flight.)  A small fold kernel adds the partial sums of the column / row slices in a fixed order and
 // scatters them to dL/dh, dL/dW2, dL/db2: deterministic, no atomics.
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -49,7 +51,7 @@ constexpr int kTileBytes = 16 * 1024;           // a chunk of g: [128 x 32] (mod
 constexpr int kSmallBytes = kNB * 32 * 4;       // the matching chunk of the small operand: 48 rows x 32 k, K-major
 constexpr int kStageBytes = 2 * kTileBytes + 2 * kSmallBytes;  // g hi, g lo, small hi, small lo
 constexpr int kTxBytes = kTileBytes + 2 * kSmallBytes;         // what TMA delivers per stage
-constexpr int kTmemCols = 64;                   // power of two >= kNB
+constexpr int kTmemCols = 128;                  // power of two >= 2 kNB: columns [0,48) hi*hi + lo*hi, [48,96) hi*lo
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t mb, int count) {
@@ -86,15 +88,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
     d |= (uint64_t)(layout_type & 7) << 61;
     return d;
 }
-// instruction descriptor: D = F32, A = B = TF32, M = 128, N = 48, majors as given (0 = K-major, 1 = MN-major)
-__device__ __forceinline__ uint32_t make_idesc(int a_mn, int b_mn) {
+// instruction descriptor: D = F32, A = B = TF32, M = 128, N = n, majors as given (0 = K-major, 1 = MN-major)
+__device__ __forceinline__ uint32_t make_idesc(int a_mn, int b_mn, int n) {
     uint32_t d = 0;
     d |= 1u << 4;                    // c_format = F32
     d |= 2u << 7;                    // a_format = TF32
     d |= 2u << 10;                   // b_format = TF32
     d |= (uint32_t)(a_mn & 1) << 15;
     d |= (uint32_t)(b_mn & 1) << 16;
-    d |= (uint32_t)(kNB >> 3) << 17;  // N
+    d |= (uint32_t)(n >> 3) << 17;    // N
     d |= (uint32_t)(128 >> 4) << 24;  // M
     return d;
 }
@@ -178,7 +180,11 @@ __global__ void __launch_bounds__(kThreads, 1)
         __syncwarp();
     } else if (warp == 4) {
         // ------------------------------------------------ MMA issuer (one lane)
-        const uint32_t idesc = make_idesc(MODE, 0);
+        // The hi and lo tiles of the small operand lie back to back (48 rows = six 1024-byte swizzle groups each), so
+        // one MMA with N = 96 multiplies the tile of g by both: A_hi [B_hi | B_lo] -> columns [0, 96), then
+        // A_lo B_hi -> columns [0, 48).  Two reads of a g tile per chunk instead of three: the kernel is bound by
+        // shared-memory bandwidth (TMA fill + split + operand reads), not by the tensor pipe.
+        const uint32_t idesc2 = make_idesc(MODE, 0, 2 * kNB), idesc1 = make_idesc(MODE, 0, kNB);
         if (lane == 0) {
             uint32_t acc = 0;
             for (int c = 0; c < nchunks; ++c) {
@@ -186,11 +192,12 @@ __global__ void __launch_bounds__(kThreads, 1)
                 mbar_wait(cvt_full0 + 8 * s, (uint32_t)(c / kStages) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_hi = stage0 + (uint32_t)s * kStageBytes, a_lo = a_hi + kTileBytes;
-                const uint32_t b_hi = a_hi + 2 * kTileBytes, b_lo = b_hi + kSmallBytes;
+                const uint32_t b_hi = a_hi + 2 * kTileBytes;
                 if (!(flags & 1u))
 #pragma unroll
-                for (int term = 0; term < 3; ++term) {  // hi*hi, hi*lo, lo*hi
-                    const uint32_t ab = (term == 2) ? a_lo : a_hi, bb = (term == 1) ? b_lo : b_hi;
+                for (int term = 0; term < 2; ++term) {  // hi * [hi | lo], lo * hi
+                    const uint32_t ab = (term == 1) ? a_lo : a_hi, bb = b_hi;
+                    const uint32_t idesc = (term == 1) ? idesc1 : idesc2;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {    // 32 k per chunk, 8 per MMA
                         // K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart; 8 k = 32 B along the row
@@ -223,7 +230,9 @@ __global__ void __launch_bounds__(kThreads, 1)
                 h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
                 h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
                 h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
-                if (!(flags & 4u)) *p = h;  // (flag 4: leave the raw FP32 tile and rely on the tensor core truncating it)
+                // The raw FP32 tile itself serves as the hi operand: kind::tf32 reads the upper 19 bits of each word, i.e.
+                // exactly the mask above (measured: results bit-identical with and without storing h; flag 4 stores it).
+                if (flags & 4u) *p = h;
                 p[kTileBytes / 16] = l;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
@@ -236,18 +245,24 @@ __global__ void __launch_bounds__(kThreads, 1)
         float* out = partial + ((size_t)slice * ((MODE == 0) ? M : N) + mn0 + row) * kNB;
 #pragma unroll
         for (int cb = 0; cb < kNB; cb += 16) {
-            uint32_t v[16];
+            uint32_t v[16], w[16];
             const uint32_t ta = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                 : "r"(ta));
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]),
+                  "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+                : "r"(ta + (uint32_t)kNB));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int i = 0; i < 16; i += 4)
-                *reinterpret_cast<float4*>(out + cb + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
-                                                                       __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+            for (int i = 0; i < 16; i += 4)  // (hi*hi + lo*hi) + hi*lo
+                *reinterpret_cast<float4*>(out + cb + i) = make_float4(
+                    __uint_as_float(v[i]) + __uint_as_float(w[i]), __uint_as_float(v[i + 1]) + __uint_as_float(w[i + 1]),
+                    __uint_as_float(v[i + 2]) + __uint_as_float(w[i + 2]), __uint_as_float(v[i + 3]) + __uint_as_float(w[i + 3]));
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
@@ -325,7 +340,9 @@ static void g2_slices(int M, int N, int& SN, int& SM) {
     // mode 0 launches (M / 128) x SN CTAs, mode 1 (N / 128) x SM.  Slices also bound the length of one tensor-memory
     // accumulation (the FP32 accumulator loses ~4e-5 relative over 10^4 terms; the fold kernel adds the slices in FP32)
     // and even out the waves over the 148 SMs: aim at >= 4 waves.  Overridable for experiments (QEC_G2_SN / QEC_G2_SM).
-    // (measured at M = 8192, N = 20480: 16 x 8 slices: 405 us, errors 1e-5 / 8e-6; 4 x 2: 433 us, 4e-5 / 3e-5)
+    // (measured at M = 8192, N = 20480 with three MMAs per k step: 16 x 8 slices: 405 us, errors 1e-5 / 8e-6; 4 x 2: 433 us,
+    // 4e-5 / 3e-5.  With the hi*hi and hi*lo products merged into one N = 96 MMA: 341 us, 7e-6 / 5e-6; the same launches
+    // with the MMAs and the split compiled out, i.e. TMA streaming alone: 305 us)
     SN = 1;
     while (((M / 128) * SN < 4 * 148 || N / SN > 1280) && (N / (2 * SN)) % 32 == 0 && N / (2 * SN) >= 256 && SN < 16) SN *= 2;
     SM = 1;

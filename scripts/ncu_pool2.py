@@ -21,10 +21,14 @@ tb = torch.randn(1, O, 4, 1, generator=g)
 t_oqi = (tb + 0.25 * torch.randn(B * P * K, O, 4, I, generator=g)).reshape(B * P * K, 4 * I * O).to(dev)
 alpha = torch.ones(1, device=dev)
 beta = torch.ones(1, device=dev)
+h = torch.randn(B * P * K, O, generator=g).to(dev)
+W2 = (torch.randn(4 * I * O, O, generator=g) / 6).to(dev)
+perm = torch.randperm(4 * I * O, generator=g).to(dev)
 with torch.no_grad():
-    for _ in range(3):
+    for _ in range(3):  # the training step's pool2 kernels: forward, plain-FP32 backward, tcgen05 backward of quater_gen2
         pose, agr, poses_all, stats = QF.routing_fused_forward_raw(t_oqi, lrfs, act, alpha, beta, T)
-        QF.routing_fused_backward_raw(t_oqi, lrfs, act, alpha, beta, poses_all, stats, torch.ones_like(pose),
-                                      torch.ones_like(agr), T, True, True, split=True)
+        g_t, _, _, _ = QF.routing_fused_backward_raw(t_oqi, lrfs, act, alpha, beta, poses_all, stats, torch.ones_like(pose),
+                                                     torch.ones_like(agr), T, True, True, split=False)
+        QF.gen2_backward(g_t, h, W2, perm)
 torch.cuda.synchronize()
 print("ok")
