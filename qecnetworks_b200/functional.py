@@ -287,6 +287,79 @@ def gen2_backward(g, h, W2, perm, need_h=True, need_w=True):
     return g_h, g_W2, g_b2
 
 
+def linear_supported(C, O):
+    return bool(_lib.query("qec_linear_supported", int(C), int(O)))
+
+
+class LinearSmall(torch.autograd.Function):
+    """y = x W^T + b for a narrow layer (O <= 64 out features): quater_gen1 of the pool2 regime (reference
+    qec_module.py:123) on the package's own FP32 kernels -- one launch forward, two backward (qec_linear_fwd / _bwd)
+    instead of the library's badly shaped SGEMMs + split-K reduction + column sum."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        M, C = x.shape
+        O = weight.shape[0]
+        x = _check(x, "x", (M, C))
+        weight = _check(weight, "weight", (O, C))
+        bias = _check(bias, "bias", (O,))
+        y = torch.empty(M, O, device=x.device, dtype=torch.float32)
+        launch("qec_linear_fwd", x, weight, bias, y, M, C, O)
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        M, C = x.shape
+        O = weight.shape[0]
+        g = _check(g, "g", (M, O))
+        need_x, need_w, need_b = ctx.needs_input_grad
+        dev = x.device
+        ws = torch.empty(int(_lib.query("qec_linear_bwd_workspace", M, C, O)), device=dev, dtype=torch.float32)
+        g_x = torch.empty_like(x) if need_x else None
+        g_w = torch.empty_like(weight) if need_w else None
+        g_b = torch.empty(O, device=dev, dtype=torch.float32) if need_b else None
+        launch("qec_linear_bwd", x, weight, g, g_x, g_w, g_b, ws, M, C, O)
+        return g_x, g_w, g_b
+
+
+def compose_supported(C):
+    return bool(_lib.query("qec_compose_supported", int(C)))
+
+
+class ComposeLinears(torch.autograd.Function):
+    """(W1 [O,C], b1 [O], W2 [R,O], b2 [R]) -> (Wc = W2 W1 [R,C], bc = W2 b1 + b2 [R]): the two Linears of get_votes
+    composed (reference qec_module.py:123-124: no non-linearity between them), one launch each way."""
+
+    @staticmethod
+    def forward(ctx, W1, b1, W2, b2):
+        O, C = W1.shape
+        R = W2.shape[0]
+        W1 = _check(W1, "W1", (O, C))
+        b1 = _check(b1, "b1", (O,))
+        W2 = _check(W2, "W2", (R, O))
+        b2 = _check(b2, "b2", (R,))
+        Wc = torch.empty(R, C, device=W1.device, dtype=torch.float32)
+        bc = torch.empty(R, device=W1.device, dtype=torch.float32)
+        launch("qec_compose_fwd", W1, b1, W2, b2, Wc, bc, R, O, C)
+        ctx.save_for_backward(W1, b1, W2)
+        return Wc, bc
+
+    @staticmethod
+    def backward(ctx, g_Wc, g_bc):
+        W1, b1, W2 = ctx.saved_tensors
+        O, C = W1.shape
+        R = W2.shape[0]
+        g_Wc = _check(g_Wc, "g_Wc", (R, C))
+        g_bc = _check(g_bc, "g_bc", (R,))
+        g_W1 = torch.empty_like(W1)
+        g_b1 = torch.empty_like(b1)
+        g_W2 = torch.empty_like(W2)
+        launch("qec_compose_bwd", W1, b1, W2, g_Wc, g_bc, g_W1, g_b1, g_W2, R, O, C)
+        return g_W1, g_b1, g_W2, g_bc
+
+
 class ClassPoseLoss(torch.autograd.Function):
     """(x [S,B,C] | None, labels [B], pose [2,B,C,4] | None) -> loss [3] = {total, spread, pose_diff}: the spread
     loss of S branches (reference qec_net.py:53-59 / qec_sia_net.py:69-77) + w_pose x the pose-difference loss on

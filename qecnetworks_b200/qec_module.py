@@ -121,6 +121,8 @@ class _SplitTf32Matmul(torch.autograd.Function):
 import os as _os
 
 GEN2_BACKWARD_TCGEN05 = _os.environ.get("QEC_GEN2_TC", "1") != "0"
+# quater_gen1 (O <= 64) and the composition of the two Linears on the package's own FP32 kernels (1) or on cuBLAS (0)
+OWN_SMALL_LINEARS = _os.environ.get("QEC_OWN_LINEARS", "1") != "0"
 
 
 def _chunks(n, length=1024):
@@ -279,8 +281,9 @@ class QecModule(Module):
             # register-resident kernel evaluate Wc x + bc per vote -- no [B*P*K, 4*O] tensor, no GEMM
             W1, b1 = self.quater_gen1.weight, self.quater_gen1.bias
             W2, b2 = self.quater_gen2.weight, self.quater_gen2.bias
+            compose = QF.ComposeLinears if (OWN_SMALL_LINEARS and QF.compose_supported(W1.shape[1])) else _ComposeFP32
             if param_grad:
-                Wc, bc = _ComposeFP32.apply(W1, b1, W2, b2)
+                Wc, bc = compose.apply(W1, b1, W2, b2)
             else:
                 # inference: the composition depends on the parameters only -- keep it until one of them changes
                 # (tensor version counters / storage), two launches less per forward
@@ -288,13 +291,14 @@ class QecModule(Module):
                 cached = getattr(self, "_composed", None)
                 if cached is None or cached[0] != key:
                     with torch.no_grad():
-                        cached = (key, _ComposeFP32.apply(W1, b1, W2, b2))
+                        cached = (key, compose.apply(W1, b1, W2, b2))
                     self._composed = cached
                 Wc, bc = cached[1]
             pose, agreement = QF.routing_small(xrot, lrfs, act_flat, Wc, bc, self.alpha, self.beta,
                                                self.num_iterations)
             return pose.squeeze(-2), agreement
-        h = _LinearFP32.apply(xrot.view(B * P * K, 3 * I), self.quater_gen1.weight, self.quater_gen1.bias)
+        linear1 = QF.LinearSmall if (OWN_SMALL_LINEARS and QF.linear_supported(3 * I, O)) else _LinearFP32
+        h = linear1.apply(xrot.view(B * P * K, 3 * I), self.quater_gen1.weight, self.quater_gen1.bias)
         if K * I >= self.FUSED_MIN_VOTES and QF.routing_fused_supported(K, I, O, self.num_iterations):
             # capsule-major transforms straight out of the GEMM; votes never touch HBM
             if QF.routing_fused_packed_supported(K, I, O, self.num_iterations):

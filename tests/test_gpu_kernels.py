@@ -832,3 +832,60 @@ def test_gen2_backward_tcgen05(M, N, Kc):
     again = QF.gen2_backward(g, h, W2, perm)
     assert all(torch.equal(a, b) for a, b in zip(again, (g_h, g_W2, g_b2)))   # no atomics: bit-reproducible
     assert not QF.gen2_bwd_supported(100, 128, 40) and not QF.gen2_bwd_supported(128, 128, 48)
+
+
+@pytest.mark.parametrize("M,C,O", [(8192, 384, 40), (100, 9, 5), (130, 7, 64), (64, 130, 17), (1, 3, 1)])
+def test_linear_small_vs_float64(M, C, O):
+    """qec_linear_fwd / _bwd (quater_gen1, reference qec_module.py:123 = nn.Linear + its autograd backward) against a
+    float64 matmul: full and ragged row blocks, in-feature counts off the 4-float grid, O up to the 64 served"""
+    from qecnetworks_b200 import functional as QF
+
+    DEV = cuda()
+    gen = torch.Generator().manual_seed(M * 7 + C)
+    x = torch.randn(M, C, generator=gen).to(DEV).requires_grad_(True)
+    W = (torch.randn(O, C, generator=gen) / C ** 0.5).to(DEV).requires_grad_(True)
+    b = torch.randn(O, generator=gen).to(DEV).requires_grad_(True)
+    g = torch.randn(M, O, generator=gen).to(DEV)
+    assert QF.linear_supported(C, O)
+    y = QF.LinearSmall.apply(x, W, b)
+    y.backward(g)
+    xd, Wd, bd = (t.detach().double().requires_grad_(True) for t in (x, W, b))
+    yd = torch.nn.functional.linear(xd, Wd, bd)
+    yd.backward(g.double())
+    for name, got, ref in (("y", y, yd), ("g_x", x.grad, xd.grad), ("g_W", W.grad, Wd.grad), ("g_b", b.grad, bd.grad)):
+        e = float((got.double() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+        print("linear margin %s M=%d C=%d O=%d err=%.2e tol=1.00e-05" % (name, M, C, O, e))
+        assert e < 1e-5, (name, e)
+    # partial outputs: input gradient only / parameter gradients only
+    x2 = x.detach().clone().requires_grad_(True)
+    QF.LinearSmall.apply(x2, W.detach(), b.detach()).backward(g)
+    assert torch.equal(x2.grad, x.grad)
+    W2 = W.detach().clone().requires_grad_(True)
+    QF.LinearSmall.apply(x.detach(), W2, b.detach()).backward(g)
+    assert torch.equal(W2.grad, W.grad)
+
+
+@pytest.mark.parametrize("R,O,C", [(512, 128, 3), (20, 5, 3), (64, 33, 12), (4, 1, 16)])
+def test_compose_linears_vs_float64(R, O, C):
+    """qec_compose_fwd / _bwd: Wc = W2 W1, bc = W2 b1 + b2 (reference qec_module.py:123-124 composed) and its adjoint"""
+    from qecnetworks_b200 import functional as QF
+
+    DEV = cuda()
+    gen = torch.Generator().manual_seed(R + O + C)
+    W1 = torch.randn(O, C, generator=gen).to(DEV).requires_grad_(True)
+    b1 = torch.randn(O, generator=gen).to(DEV).requires_grad_(True)
+    W2 = (torch.randn(R, O, generator=gen) / O ** 0.5).to(DEV).requires_grad_(True)
+    b2 = torch.randn(R, generator=gen).to(DEV).requires_grad_(True)
+    gW = torch.randn(R, C, generator=gen).to(DEV)
+    gb = torch.randn(R, generator=gen).to(DEV)
+    assert QF.compose_supported(C)
+    Wc, bc = QF.ComposeLinears.apply(W1, b1, W2, b2)
+    torch.autograd.backward([Wc, bc], [gW, gb])
+    d = [t.detach().double().requires_grad_(True) for t in (W1, b1, W2, b2)]
+    Wcd, bcd = d[2] @ d[0], d[2] @ d[1] + d[3]
+    torch.autograd.backward([Wcd, bcd], [gW.double(), gb.double()])
+    pairs = [("Wc", Wc, Wcd), ("bc", bc, bcd)] + [("g_" + n, t.grad, td.grad) for n, t, td in zip(("W1", "b1", "W2", "b2"), (W1, b1, W2, b2), d)]
+    for name, got, ref in pairs:
+        e = float((got.double() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+        print("compose margin %s R=%d O=%d C=%d err=%.2e tol=1.00e-05" % (name, R, O, C, e))
+        assert e < 1e-5, (name, e)
