@@ -404,7 +404,8 @@ def run_b200(a):
     net = qb.QecNet(2048, a.channels, a.classes, a.iters).to(dev)
     ddp.broadcast_parameters(net, 0)
     # pool2's gradients (90 % of the bytes) are all-reduced while the pool1 backward still runs
-    bucket = ddp.FlatGradBucket(net.parameters(), early=list(net.pool2.parameters()))
+    # direct: the backward kernels write the parameter gradients straight into the flat buffer (no per-parameter add)
+    bucket = ddp.FlatGradBucket(net.parameters(), early=list(net.pool2.parameters()), direct=True)
     # train_cls.py:44-51 (Adam, default betas/eps): one launch over the flat buffers, which also applies the
     # 1/world of the all-reduce and re-zeroes the gradient buffer (tests/test_gpu_adam.py: == torch.optim.Adam)
     opt = ddp.FlatAdam(bucket, lr=1e-3)

@@ -211,7 +211,7 @@ int qec_gen2_bwd(const float* g, const float* h, const float* W2, const long lon
  *   qec_linear_bwd:  g [M, O] -> g_x [M, C] | NULL, g_W [O, C] | NULL, g_b [O] | NULL;
  *                    workspace: qec_linear_bwd_workspace(M, C, O) floats
  *   qec_compose_fwd: Wc [R, C] = W2 [R, O] W1 [O, C],  bc [R] = W2 b1 + b2        (C <= 16: qec_compose_supported)
- *   qec_compose_bwd: (g_Wc, g_bc) -> g_W1 [O, C], g_b1 [O], g_W2 [R, O]           (dL/db2 is g_bc itself) */
+ *   qec_compose_bwd: (g_Wc, g_bc) -> g_W1 [O, C], g_b1 [O], g_W2 [R, O], g_b2 [R] | NULL  (dL/db2 = g_bc, copied) */
 int qec_linear_supported(int C, int O);
 long long qec_linear_bwd_workspace(int M, int C, int O);
 int qec_linear_fwd(const float* x, const float* W, const float* b, float* y, int M, int C, int O, void* stream);
@@ -221,7 +221,7 @@ int qec_compose_supported(int C);
 int qec_compose_fwd(const float* W1, const float* b1, const float* W2, const float* b2, float* Wc, float* bc, int R, int O,
                     int C, void* stream);
 int qec_compose_bwd(const float* W1, const float* b1, const float* W2, const float* g_Wc, const float* g_bc, float* g_W1,
-                    float* g_b1, float* g_W2, int R, int O, int C, void* stream);
+                    float* g_b1, float* g_W2, float* g_b2, int R, int O, int C, void* stream);
 
 /* Spread loss of QEC-Net and its gradient in one launch pair (reference models/qec_net.py:53-59,
  * margin 0.1): loss [1] = mean_b sum_{c != y_b} relu(m - (x[b,y_b] - x[b,c]))^2, g_x [B, C] = dloss/dx.

@@ -55,7 +55,7 @@ SIGNATURES = {
     "qec_linear_bwd": ([_P] * 7 + [_I, _I, _I, _P], lambda a: 1 + (1 if (a[4] or a[5]) else 0)),
     "qec_compose_supported": ([_I], 0),
     "qec_compose_fwd": ([_P] * 6 + [_I, _I, _I, _P], 1),
-    "qec_compose_bwd": ([_P] * 8 + [_I, _I, _I, _P], 1),
+    "qec_compose_bwd": ([_P] * 9 + [_I, _I, _I, _P], 1),
     "qec_class_pose_loss": ([_P, _P, _F, _P, _F, _P, _P, _P, _P, _I, _I, _I, _P], 1),
     "qec_quat_eval": ([_P, _P, _P, _P, _LL, _P], 1),
     "qec_adam_flat": ([_P, _P, _P, _P, _LL, _F, _D, _D, _F, _F, _F, _I, _P, _P], 1),

@@ -297,13 +297,15 @@ constexpr int kCbThreads = 512;
 __global__ void __launch_bounds__(kCbThreads)
     compose_bwd_kernel(const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
                        const float* __restrict__ g_Wc, const float* __restrict__ g_bc, float* __restrict__ g_W1,
-                       float* __restrict__ g_b1, float* __restrict__ g_W2, int R, int O, int C, int nA) {
+                       float* __restrict__ g_b1, float* __restrict__ g_W2, float* __restrict__ g_b2, int R, int O, int C,
+                       int nA) {
     __shared__ float red[kCbThreads / 32][kCMax + 1][32];
     constexpr int NW = kCbThreads / 32;
     if ((int)blockIdx.x < nA) {
         const long long e = (long long)blockIdx.x * kCbThreads + threadIdx.x;
         if (e >= (long long)R * O) return;
         const int r = (int)(e / O), o = (int)(e % O);
+        if (g_b2 != nullptr && o == 0) g_b2[r] = __ldg(g_bc + r);  // dL/db2 = dL/dbc
         float s = __ldg(g_bc + r) * __ldg(b1 + o);
 #pragma unroll
         for (int c = 0; c < kCMax; ++c)
@@ -463,9 +465,10 @@ extern "C" int qec_compose_fwd(const float* W1, const float* b1, const float* W2
     return launch_status();
 }
 
-// adjoint: (g_Wc [R, C], g_bc [R]) -> g_W1 [O, C], g_b1 [O], g_W2 [R, O]   (dL/db2 = g_bc itself)
+// adjoint: (g_Wc [R, C], g_bc [R]) -> g_W1 [O, C], g_b1 [O], g_W2 [R, O], g_b2 [R] | NULL (dL/db2 = g_bc: a copy, for
+// callers that want it somewhere else, e.g. inside a flat gradient buffer)
 extern "C" int qec_compose_bwd(const float* W1, const float* b1, const float* W2, const float* g_Wc, const float* g_bc,
-                               float* g_W1, float* g_b1, float* g_W2, int R, int O, int C, void* stream) {
+                               float* g_W1, float* g_b1, float* g_W2, float* g_b2, int R, int O, int C, void* stream) {
     QEC_CHECK_ARG(W1, 1);
     QEC_CHECK_ARG(b1, 2);
     QEC_CHECK_ARG(W2, 3);
@@ -474,10 +477,10 @@ extern "C" int qec_compose_bwd(const float* W1, const float* b1, const float* W2
     QEC_CHECK_ARG(g_W1, 6);
     QEC_CHECK_ARG(g_b1, 7);
     QEC_CHECK_ARG(g_W2, 8);
-    QEC_CHECK_ARG(R >= 1 && O >= 1, 9);
-    QEC_CHECK_ARG(qec_compose_supported(C), 11);
+    QEC_CHECK_ARG(R >= 1 && O >= 1, 10);
+    QEC_CHECK_ARG(qec_compose_supported(C), 12);
     const int nA = (int)(((long long)R * O + lin::kCbThreads - 1) / lin::kCbThreads), nB = (O + 31) / 32;
-    lin::compose_bwd_kernel<<<nA + nB, lin::kCbThreads, 0, static_cast<cudaStream_t>(stream)>>>(W1, b1, W2, g_Wc, g_bc, g_W1, g_b1, g_W2,
-                                                                                    R, O, C, nA);
+    lin::compose_bwd_kernel<<<nA + nB, lin::kCbThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        W1, b1, W2, g_Wc, g_bc, g_W1, g_b1, g_W2, g_b2, R, O, C, nA);
     return launch_status();
 }

@@ -61,7 +61,7 @@ class FlatGradBucket:
     Protocol per step: zero() -> forward -> backward -> all_reduce_mean(); a backward that is NOT
     followed by all_reduce_mean() must run with `overlap = False`."""
 
-    def __init__(self, params, early=None, group=None):
+    def __init__(self, params, early=None, group=None, direct=False):
         params = [p for p in params if p.requires_grad]
         if not params:
             raise ValueError("no trainable parameters")
@@ -78,6 +78,19 @@ class FlatGradBucket:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             self._views.append((p, off))
             off += p.numel()
+        # direct: the backward kernels write parameter gradients straight into this buffer (no AccumulateGrad add per
+        # parameter: 12 launches of the QEC-Net step).  Each parameter gets a "home"; release() drops the .grad views
+        # so that the next backward hands the homes to the kernels and autograd adopts what they return as .grad.
+        # Valid when every parameter enters the graph once per backward (a second use falls back to autograd's own
+        # sum, which leaves the buffer: all_reduce_mean() / check_views() raise) and the buffer is zero when the
+        # backward starts (FlatAdam leaves it so; otherwise zero()).
+        self.direct = bool(direct)
+        if self.direct:
+            from .functional import GradHome
+
+            for p, off in self._views:
+                p._qec_grad_home = GradHome(self.flat, off)
+            self.release()
         self._seen = 0
         self._work = None
         self._group = group  # fixed at construction: the hooks and all_reduce_mean() use the same one
@@ -107,12 +120,22 @@ class FlatGradBucket:
                     "optimizer.zero_grad() called with set_to_none=True?): use bucket.zero() or "
                     "zero_grad(set_to_none=False), otherwise the all-reduce would exchange a stale buffer")
 
+    def release(self):
+        """direct mode: forget the .grad tensors (they alias the buffer, nothing is freed) and re-arm the homes"""
+        for p, _ in self._views:
+            p.grad = None
+            home = getattr(p, "_qec_grad_home", None)
+            if home is not None:
+                home.taken = False
+
     def zero(self):
         if self._work is not None:  # a reduction nobody joined: finish it before the buffer is reused
             self._work.wait()
             self._work = None
         self.flat.zero_()
         self._seen = 0
+        if self.direct:
+            self.release()
 
     def all_reduce_mean(self, group=None, average=True):
         """sum over ranks / world size: the loss is a mean over the GLOBAL batch.  With average=False the
@@ -185,6 +208,8 @@ class FlatAdam:
         _lib.launch("qec_adam_flat", self.flat, self.bucket.flat, self.exp_avg, self.exp_avg_sq,
                     self.flat.numel(), self.lr, float(self.betas[0]), float(self.betas[1]), self.eps, self.weight_decay,
                     float(grad_scale), 1 if self.zero_grad else 0, self.state)
+        if self.bucket.direct and self.zero_grad:
+            self.bucket.release()  # the buffer is zero again: the next backward writes into it directly
 
     def steps_taken(self):
         return int(self.state[0].item())

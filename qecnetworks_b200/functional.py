@@ -23,6 +23,58 @@ def _check(t, name, shape=None):
     return t.contiguous()
 
 
+class GradHome:
+    """Where a parameter's gradient lives inside a flat gradient buffer (ddp.FlatGradBucket(direct=True)).
+    `taken`: the home was handed to a backward node since the last release (a parameter used twice in one graph
+    gets it once; the second contribution is a fresh tensor and autograd adds the two)."""
+
+    __slots__ = ("flat", "offset", "taken")
+
+    def __init__(self, flat, offset):
+        self.flat, self.offset, self.taken = flat, int(offset), False
+
+
+def _home_out(param, numel=None):
+    """A fresh tensor aliasing `param`'s home in the flat gradient buffer, or None.  Given out only while the
+    parameter has no .grad (autograd then adopts the returned tensor as .grad without a copy or an add) and once per
+    release.  The home is all zeros at that point: the buffer is zeroed between steps (FlatAdam / bucket.zero())."""
+    home = getattr(param, "_qec_grad_home", None)
+    if home is None or home.taken or param.grad is not None or home.flat.device != param.device:
+        return None
+    n = param.numel() if numel is None else numel
+    if home.offset + n > home.flat.numel():
+        return None
+    home.taken = True
+    out = torch.empty(0, device=home.flat.device, dtype=torch.float32)
+    shape = tuple(param.shape) if numel is None else (n,)
+    out.set_(home.flat.untyped_storage(), home.flat.storage_offset() + home.offset, shape)
+    return out
+
+
+def _home_pair_out(a, b):
+    """alpha, beta -> one 2-float tensor over their (adjacent) homes, or None"""
+    ha, hb = getattr(a, "_qec_grad_home", None), getattr(b, "_qec_grad_home", None)
+    if ha is None or hb is None or ha.flat is not hb.flat or hb.offset != ha.offset + 1 or hb.taken or b.grad is not None:
+        return None
+    out = _home_out(a, 2)
+    if out is not None:
+        hb.taken = True
+    return out
+
+
+def _zeros_split(dev, *shapes):
+    """several zero tensors carved from ONE zero-filled buffer (one fill launch instead of one per tensor); a shape
+    of None yields None.  Offsets are rounded up to 4 floats so that every piece stays 16-byte aligned."""
+    sizes = [0 if sh is None else int(torch.Size(sh).numel()) for sh in shapes]
+    padded = [(n + 3) // 4 * 4 for n in sizes]
+    buf = torch.zeros(sum(padded), device=dev, dtype=torch.float32)
+    out, off = [], 0
+    for sh, n, pn in zip(shapes, sizes, padded):
+        out.append(None if sh is None else buf[off:off + n].view(sh))
+        off += pn
+    return out
+
+
 class LrfMeanRotate(torch.autograd.Function):
     """(lrfs, activation, points) -> (mean_lrf [B,P,I,4], xrot [B,P,K,I,3]).
     reference: QecModule.mean_lrf_per_patch + the qrotv at the top of get_votes
@@ -156,18 +208,21 @@ def routing_fused_forward_raw(t_oqi, lrfs, activation, alpha, beta, T):
 
 
 def routing_fused_backward_raw(t_oqi, lrfs, activation, alpha, beta, poses_all, stats, g_pose, g_agreement, T,
-                               need_lrfs, need_act, split=False):
+                               need_lrfs, need_act, split=False, g_ab=None):
     """no autograd: -> g_toqi, g_lrfs | None, g_act | None, g_alpha_beta [2].  With split=True g_toqi is a
     pair (hi, lo) of [B*P*K, 4*I*O] tensors: hi (float32) = the gradient rounded to the TF32 grid, lo
     (bfloat16) = the remainder (qec_routing_fused_bwd_split; packed-pair geometries only)."""
     B, P, K, I, _ = lrfs.shape
     O = t_oqi.shape[-1] // (4 * I)
     dev = lrfs.device
-    g_pose = torch.zeros(B, P, O, 4, device=dev) if g_pose is None else g_pose.contiguous()
-    g_agreement = torch.zeros(B, P, O, device=dev) if g_agreement is None else g_agreement.contiguous()
-    g_lrfs = torch.zeros_like(lrfs) if need_lrfs else None
-    g_act = torch.zeros_like(activation) if need_act else None
-    g_ab = torch.zeros(2, device=dev, dtype=torch.float32)
+    # everything the kernel accumulates into, and the upstream gradients autograd left out, from one zero fill
+    # (g_ab may be given by the caller: a zeroed home in the flat gradient buffer)
+    z_pose, z_agr, g_lrfs, g_act, z_ab = _zeros_split(
+        dev, (B, P, O, 4) if g_pose is None else None, (B, P, O) if g_agreement is None else None,
+        lrfs.shape if need_lrfs else None, activation.shape if need_act else None, (2,) if g_ab is None else None)
+    g_pose = z_pose if g_pose is None else g_pose.contiguous()
+    g_agreement = z_agr if g_agreement is None else g_agreement.contiguous()
+    g_ab = z_ab if g_ab is None else g_ab
     if split:
         g_toqi = (torch.empty_like(t_oqi), torch.empty(t_oqi.shape, device=dev, dtype=torch.bfloat16))
         launch("qec_routing_fused_bwd_split", t_oqi, lrfs, activation, alpha, beta,
@@ -267,7 +322,7 @@ def gen2_bwd_supported(M, N, Kc):
     return bool(_lib.query("qec_gen2_bwd_supported", int(M), int(N), int(Kc)))
 
 
-def gen2_backward(g, h, W2, perm, need_h=True, need_w=True):
+def gen2_backward(g, h, W2, perm, need_h=True, need_w=True, out_W2=None, out_b2=None):
     """Backward of quater_gen2 (reference qec_module.py:124) from the FP32 transform gradient g [M, N] on the tcgen05
     tensor cores (qec_gen2_bwd: TMA-fed, 3-term TF32 split, accumulator in tensor memory):
     -> (g_h [M, Kc] | None, g_W2 [N, Kc] | None, g_b2 [N] | None)"""
@@ -281,8 +336,8 @@ def gen2_backward(g, h, W2, perm, need_h=True, need_w=True):
     dev = g.device
     ws = torch.empty(int(_lib.query("qec_gen2_bwd_workspace", M, N, Kc)), device=dev, dtype=torch.float32)
     g_h = torch.empty(M, Kc, device=dev, dtype=torch.float32) if need_h else None
-    g_W2 = torch.empty(N, Kc, device=dev, dtype=torch.float32) if need_w else None
-    g_b2 = torch.empty(N, device=dev, dtype=torch.float32) if need_w else None
+    g_W2 = (out_W2 if out_W2 is not None else torch.empty(N, Kc, device=dev, dtype=torch.float32)) if need_w else None
+    g_b2 = (out_b2 if out_b2 is not None else torch.empty(N, device=dev, dtype=torch.float32)) if need_w else None
     launch("qec_gen2_bwd", g, h, W2, perm.contiguous(), g_h, g_W2, g_b2, ws, M, N, Kc, 0)
     return g_h, g_W2, g_b2
 
@@ -306,6 +361,7 @@ class LinearSmall(torch.autograd.Function):
         y = torch.empty(M, O, device=x.device, dtype=torch.float32)
         launch("qec_linear_fwd", x, weight, bias, y, M, C, O)
         ctx.save_for_backward(x, weight)
+        ctx.bias = bias  # (only to find its home in a flat gradient buffer)
         return y
 
     @staticmethod
@@ -318,8 +374,12 @@ class LinearSmall(torch.autograd.Function):
         dev = x.device
         ws = torch.empty(int(_lib.query("qec_linear_bwd_workspace", M, C, O)), device=dev, dtype=torch.float32)
         g_x = torch.empty_like(x) if need_x else None
-        g_w = torch.empty_like(weight) if need_w else None
-        g_b = torch.empty(O, device=dev, dtype=torch.float32) if need_b else None
+        g_w = (_home_out(weight) if need_w else None)
+        if need_w and g_w is None:
+            g_w = torch.empty_like(weight)
+        g_b = (_home_out(ctx.bias) if need_b else None)
+        if need_b and g_b is None:
+            g_b = torch.empty(O, device=dev, dtype=torch.float32)
         launch("qec_linear_bwd", x, weight, g, g_x, g_w, g_b, ws, M, C, O)
         return g_x, g_w, g_b
 
@@ -344,6 +404,7 @@ class ComposeLinears(torch.autograd.Function):
         bc = torch.empty(R, device=W1.device, dtype=torch.float32)
         launch("qec_compose_fwd", W1, b1, W2, b2, Wc, bc, R, O, C)
         ctx.save_for_backward(W1, b1, W2)
+        ctx.b2 = b2  # (only to find its home in a flat gradient buffer)
         return Wc, bc
 
     @staticmethod
@@ -353,11 +414,13 @@ class ComposeLinears(torch.autograd.Function):
         R = W2.shape[0]
         g_Wc = _check(g_Wc, "g_Wc", (R, C))
         g_bc = _check(g_bc, "g_bc", (R,))
-        g_W1 = torch.empty_like(W1)
-        g_b1 = torch.empty_like(b1)
-        g_W2 = torch.empty_like(W2)
-        launch("qec_compose_bwd", W1, b1, W2, g_Wc, g_bc, g_W1, g_b1, g_W2, R, O, C)
-        return g_W1, g_b1, g_W2, g_bc
+        g_W1, g_b1, g_W2 = (_home_out(t) for t in (W1, b1, W2))
+        g_W1 = torch.empty_like(W1) if g_W1 is None else g_W1
+        g_b1 = torch.empty_like(b1) if g_b1 is None else g_b1
+        g_W2 = torch.empty_like(W2) if g_W2 is None else g_W2
+        g_b2 = _home_out(ctx.b2)  # dL/db2 = dL/dbc: copied into b2's home when it has one, else passed through
+        launch("qec_compose_bwd", W1, b1, W2, g_Wc, g_bc, g_W1, g_b1, g_W2, g_b2, R, O, C)
+        return g_W1, g_b1, g_W2, (g_bc if g_b2 is None else g_b2)
 
 
 class ClassPoseLoss(torch.autograd.Function):
@@ -462,11 +525,13 @@ class RoutingSmall(torch.autograd.Function):
         B, P, K = activation.shape
         O = bc.shape[0] // 4
         dev = lrfs.device
-        g_pose = torch.zeros(B, P, O, 4, device=dev) if g_pose is None else g_pose.contiguous()
-        g_agreement = torch.zeros(B, P, O, device=dev) if g_agreement is None else g_agreement.contiguous()
-        g_Wc = torch.zeros_like(Wc)
-        g_bc = torch.zeros_like(bc)
-        g_ab = torch.zeros(2, device=dev, dtype=torch.float32)
+        g_ab = _home_pair_out(alpha, beta)  # straight into the flat gradient buffer when the parameters live there
+        z_pose, z_agr, g_Wc, g_bc, z_ab = _zeros_split(
+            dev, (B, P, O, 4) if g_pose is None else None, (B, P, O) if g_agreement is None else None, Wc.shape, bc.shape,
+            (2,) if g_ab is None else None)
+        g_pose = z_pose if g_pose is None else g_pose.contiguous()
+        g_agreement = z_agr if g_agreement is None else g_agreement.contiguous()
+        g_ab = z_ab if g_ab is None else g_ab
         launch("qec_routing_small_bwd", xrot, lrfs, activation, Wc, bc, alpha, beta,
              poses_all, stats, g_pose, g_agreement, g_Wc, g_bc, g_ab, B * P, K, O,
              ctx.T)

@@ -171,10 +171,13 @@ class _TransformRoutingFused(torch.autograd.Function):
         if GEN2_BACKWARD_TCGEN05 and QF.gen2_bwd_supported(t_oqi.shape[0], t_oqi.shape[1], h.shape[1]):
             # the transform gradient leaves the routing backward as plain FP32 and both products of the Linear's
             # backward run on this package's own tcgen05 kernel (csrc/gen2_bwd.cu) instead of four cuBLAS bmm's
+            # (parameter gradients go straight into the flat gradient buffer when the parameters have a home there)
             g_t, g_lrfs, g_act, g_ab = QF.routing_fused_backward_raw(
                 t_oqi, lrfs, activation, alpha, beta, poses_all, stats, g_pose, g_agreement, ctx.T,
-                ctx.needs_input_grad[4], ctx.needs_input_grad[5], split=False)
-            g_h, g_W2, g_b2 = QF.gen2_backward(g_t, h, W2, perm, need_h, need_w)
+                ctx.needs_input_grad[4], ctx.needs_input_grad[5], split=False, g_ab=QF._home_pair_out(alpha, beta))
+            g_h, g_W2, g_b2 = QF.gen2_backward(g_t, h, W2, perm, need_h, need_w,
+                                               out_W2=QF._home_out(W2) if need_w else None,
+                                               out_b2=QF._home_out(b2) if need_w else None)
             return g_h, g_W2, g_b2, None, g_lrfs, g_act, g_ab[0:1], g_ab[1:2], None
         (g_hi, g_lo), g_lrfs, g_act, g_ab = QF.routing_fused_backward_raw(
             t_oqi, lrfs, activation, alpha, beta, poses_all, stats, g_pose, g_agreement, ctx.T,

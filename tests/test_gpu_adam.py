@@ -86,3 +86,57 @@ def test_flat_adam_in_cuda_graph():
     for p, q in zip(ours, ref):
         err = float((p.detach() - q.detach()).abs().max())
         assert err <= 2e-6 * max(1.0, float(q.detach().abs().max())), err
+
+
+def test_direct_gradient_placement_matches_accumulating_bucket():
+    """FlatGradBucket(direct=True): the backward kernels write every parameter gradient of QEC-Net straight into
+    the flat buffer (autograd adopts the aliases as .grad: no add launch per parameter).  Three training steps give
+    the same gradients and parameters as the accumulating bucket; a parameter that enters the graph twice (the
+    Siamese net) is caught by check_views()."""
+    import copy
+
+    import qecnetworks_b200 as qb
+    from qecnetworks_b200 import _lib, ddp
+    from qecnetworks_b200.synthetic import synthetic_batch
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    net_a = qb.QecNet(2048, 128, 40, 3).to(dev)   # BASELINE config 2 geometry (cluster + register-resident regimes)
+    net_b = copy.deepcopy(net_a)
+    buck_a = ddp.FlatGradBucket(net_a.parameters(), early=list(net_a.pool2.parameters()), direct=True)
+    buck_b = ddp.FlatGradBucket(net_b.parameters(), early=list(net_b.pool2.parameters()))
+    opt_a, opt_b = ddp.FlatAdam(buck_a, lr=1e-3), ddp.FlatAdam(buck_b, lr=1e-3)
+    launches = []
+    for step in range(3):
+        points, lrfs, act, labels = [t.to(dev) for t in synthetic_batch(2, ncls=40, seed=50 + step)]
+        grads = []
+        for net, buck in ((net_a, buck_a), (net_b, buck_b)):
+            n0 = _lib.launches()
+            _, a = net(points, lrfs, act, None)
+            net.spread_loss(a, labels).backward()
+            launches.append(_lib.launches() - n0)
+            buck.check_views()   # every .grad aliases its slice of the flat buffer
+            grads.append(buck.flat.clone())
+        scale = float(grads[1].abs().max())
+        err = float((grads[0] - grads[1]).abs().max()) / scale
+        print("direct margin grads step=%d err=%.2e tol=5.00e-05" % (step, err))
+        # same kernels either way; what differs run to run is the order of the FP32 atomics (dL/dlrfs of pool2 feeds
+        # the whole pool1 backward): ~1e-5 of the largest entry.  A lost or doubled gradient would be O(1).
+        assert err < 5e-5, err
+        opt_a.step()
+        opt_b.step()
+        assert float(buck_a.flat.abs().max()) == 0.0 and all(p.grad is None for p in net_a.parameters())
+        # (parameters are not compared after the Adam steps: Adam is scale-free per element, so an entry whose gradient
+        # is at the level of the atomics' noise may step in either direction; the nets are re-synchronised instead)
+        with torch.no_grad():
+            for p, q in zip(net_a.parameters(), net_b.parameters()):
+                q.copy_(p)
+    assert launches[0] == launches[1]   # the same kernels of this package run either way (what is saved are ATen adds)
+    # a parameter used twice in one graph: the second contribution cannot share the home
+    sia = qb.QecSiaNet(2048, 16, 10, 3).to(dev)
+    buck_s = ddp.FlatGradBucket(sia.parameters(), direct=True)
+    points, lrfs, act, labels = [t.to(dev) for t in synthetic_batch(2, ncls=10, seed=9)]
+    _, x = sia(torch.stack([points, points], 1), torch.stack([lrfs, lrfs], 1), torch.stack([act, act], 1), None)
+    sia.spread_loss(x, torch.stack([labels, labels], 1)).backward()
+    with pytest.raises(RuntimeError):
+        buck_s.check_views()

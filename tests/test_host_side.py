@@ -233,3 +233,66 @@ def test_fused_build_selector_without_gpu():
     finally:
         lib.qec_routing_fused_set_wide(start)
     assert lib.qec_routing_fused_set_wide(-1) == start
+
+
+def test_gradient_homes_and_zero_split_host_logic():
+    """direct gradient placement (FlatGradBucket(direct=True)): a backward node gets a parameter's home in the flat
+    buffer once per release and only while the parameter has no .grad; autograd adopts the returned alias as .grad
+    without a copy (checked with a toy Function on the CPU -- the real kernels are exercised by the GPU tests)"""
+    import torch
+    from qecnetworks_b200 import ddp
+    from qecnetworks_b200 import functional as QF
+
+    a, b, c = _z(3), _z(2), _z(1)
+    ps = [torch.nn.Parameter(t + 1) for t in (a, b, c)]
+    bucket = ddp.FlatGradBucket(ps, direct=True)
+    assert all(p.grad is None for p in ps)
+
+    class Toy(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, p, q, x):
+            ctx.save_for_backward(p, q, x)
+            return (p * x).sum() + q.sum() * 2.0
+
+        @staticmethod
+        def backward(ctx, g):
+            p, q, x = ctx.saved_tensors
+            gp = QF._home_out(p)
+            assert gp is not None and float(gp.abs().max()) == 0.0   # zeroed home
+            gp.copy_(x * g)
+            assert QF._home_out(p) is None                          # handed out once per release
+            gq = QF._home_out(q)
+            gq.fill_(2.0 * float(g))
+            return gp, gq, None
+
+    x = torch.tensor([1.0, 2.0, 3.0])
+    Toy.apply(ps[0], ps[1], x).backward()
+    base = bucket.flat.data_ptr()
+    assert ps[0].grad.data_ptr() == base and ps[1].grad.data_ptr() == base + 12
+    assert bucket.flat.tolist() == [1.0, 2.0, 3.0, 2.0, 2.0, 0.0]
+    assert QF._home_out(ps[0]) is None                              # .grad exists: autograd must accumulate instead
+    with pytest.raises(RuntimeError):
+        bucket.check_views()                                        # ps[2] got no gradient: not a view of the buffer
+    bucket.zero()                                                   # zero + release
+    assert all(p.grad is None for p in ps) and float(bucket.flat.abs().max()) == 0.0
+    assert QF._home_out(ps[2]) is not None
+    # alpha/beta pairs: adjacent homes give one 2-float tensor
+    bucket.release()
+    pair = QF._home_pair_out(ps[1], ps[2])
+    assert pair is None                                             # ps[1] has 2 elements: ps[2] is not at offset + 1
+    al, be = torch.nn.Parameter(torch.ones(1)), torch.nn.Parameter(torch.ones(1))
+    b2 = ddp.FlatGradBucket([al, be], direct=True)
+    pair = QF._home_pair_out(al, be)
+    assert pair is not None and pair.shape == (2,) and pair.data_ptr() == b2.flat.data_ptr()
+    assert QF._home_pair_out(al, be) is None
+    # one zero fill, several tensors, 16-byte aligned pieces, None passes through
+    z = QF._zeros_split(torch.device("cpu"), (2, 3), None, (5,), (1,))
+    assert z[1] is None and [tuple(t.shape) for t in (z[0], z[2], z[3])] == [(2, 3), (5,), (1,)]
+    assert all(t.data_ptr() % 16 == 0 and float(t.abs().max()) == 0.0 for t in (z[0], z[2], z[3]))
+    assert z[2].data_ptr() - z[0].data_ptr() == 32 and z[3].data_ptr() - z[2].data_ptr() == 32
+
+
+def _z(n):
+    import torch
+
+    return torch.zeros(n)
