@@ -277,7 +277,11 @@ class QecModule(Module):
         _, xrot = QF.lrf_mean_rotate(lrfs, activation, points)
         act_flat = activation.view(B, P, K * I)
         data_grad = torch.is_grad_enabled() and (points.requires_grad or lrfs.requires_grad or activation.requires_grad)
-        param_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        # (the tensors themselves, not self.parameters(): the replicas nn.DataParallel builds hold their parameters as
+        # plain non-leaf tensors and list none)
+        own = (self.quater_gen1.weight, self.quater_gen1.bias, self.quater_gen2.weight, self.quater_gen2.bias,
+               self.alpha, self.beta)
+        param_grad = torch.is_grad_enabled() and any(t.requires_grad for t in own)
         small = QF.routing_small_supported(K, I, O, self.num_iterations) if I == 1 else 0
         if not data_grad and (small == 1 or (small == 2 and not param_grad)):
             # no non-linearity between the two Linears: compose them (rank 3 for I = 1) and let the
