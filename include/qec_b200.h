@@ -203,6 +203,17 @@ long long qec_gen2_bwd_workspace(int M, int N, int Kc);
 int qec_gen2_bwd(const float* g, const float* h, const float* W2, const long long* perm, float* g_h, float* g_W2,
                  float* g_b2, float* workspace, int M, int N, int Kc, int variant, void* stream);
 
+/* ---- forward of quater_gen2 on the tcgen05 tensor cores ---------------------------------------------------------
+ * reference models/qec_module.py:124 (nn.Linear(O, 4*I*O) forward, bias included), output columns permuted:
+ *   t [M, N] = h [M, Kc] W2[perm]^T + b2[perm]     (W2 [N, Kc], b2 [N] in the reference's row order; perm [N] int64
+ *   | NULL = row of W2 / b2 behind output column n).  TMA-fed, 3-term TF32 split at FP32 accuracy, accumulators in
+ * tensor memory, persistent CTAs.  workspace: qec_gen2_fwd_workspace(M, N, Kc) floats.
+ * Supported (qec_gen2_fwd_supported): M, N multiples of 128, Kc <= 63. */
+int qec_gen2_fwd_supported(int M, int N, int Kc);
+long long qec_gen2_fwd_workspace(int M, int N, int Kc);
+int qec_gen2_fwd(const float* h, const float* W2, const float* b2, const long long* perm, float* t, float* workspace,
+                 int M, int N, int Kc, void* stream);
+
 /* ---- narrow FP32 Linear (out features O <= 64) and the composition of the two Linears of get_votes ----------------
  * reference models/qec_module.py:123 (quater_gen1 = nn.Linear(3*I, O), forward and autograd backward) and :123-124
  * (quater_gen2(quater_gen1(x)) with no non-linearity in between: for I = 1 the register-resident kernels evaluate the

@@ -49,6 +49,9 @@ SIGNATURES = {
     "qec_gen2_bwd_workspace": ([_I, _I, _I], 0),
     "qec_gen2_bwd": ([_P] * 8 + [_I, _I, _I, _I, _P], lambda a: 2 + (1 if a[4] else 0) + (1 if a[5] else 0)),
     "qec_spread_loss": ([_P, _P, _F, _P, _P, _P, _P, _I, _I, _P], 2),
+    "qec_gen2_fwd_supported": ([_I, _I, _I], 0),
+    "qec_gen2_fwd_workspace": ([_I, _I, _I], 0),
+    "qec_gen2_fwd": ([_P] * 6 + [_I, _I, _I, _P], 2),
     "qec_linear_supported": ([_I, _I], 0),
     "qec_linear_bwd_workspace": ([_I, _I, _I], 0),
     "qec_linear_fwd": ([_P] * 4 + [_I, _I, _I, _P], 1),

@@ -322,6 +322,26 @@ def gen2_bwd_supported(M, N, Kc):
     return bool(_lib.query("qec_gen2_bwd_supported", int(M), int(N), int(Kc)))
 
 
+def gen2_fwd_supported(M, N, Kc):
+    return bool(_lib.query("qec_gen2_fwd_supported", int(M), int(N), int(Kc)))
+
+
+def gen2_forward(h, W2, b2, perm=None):
+    """t [M, N] = h W2[perm]^T + b2[perm]: quater_gen2 (reference qec_module.py:124) on the tcgen05 tensor cores at
+    FP32 accuracy (qec_gen2_fwd), output columns in the order `perm` gives (capsule-major for the cluster kernels)"""
+    M, Kc = h.shape
+    N = W2.shape[0]
+    h = _check(h, "h", (M, Kc))
+    W2 = _check(W2, "W2", (N, Kc))
+    b2 = _check(b2, "b2", (N,))
+    if perm is not None and (perm.dtype != torch.int64 or not perm.is_cuda):
+        raise TypeError("perm must be a CUDA int64 tensor")
+    ws = torch.empty(int(_lib.query("qec_gen2_fwd_workspace", M, N, Kc)), device=h.device, dtype=torch.float32)
+    t = torch.empty(M, N, device=h.device, dtype=torch.float32)
+    launch("qec_gen2_fwd", h, W2, b2, None if perm is None else perm.contiguous(), t, ws, M, N, Kc)
+    return t
+
+
 def gen2_backward(g, h, W2, perm, need_h=True, need_w=True, out_W2=None, out_b2=None):
     """Backward of quater_gen2 (reference qec_module.py:124) from the FP32 transform gradient g [M, N] on the tcgen05
     tensor cores (qec_gen2_bwd: TMA-fed, 3-term TF32 split, accumulator in tensor memory):

@@ -121,6 +121,11 @@ class _SplitTf32Matmul(torch.autograd.Function):
 import os as _os
 
 GEN2_BACKWARD_TCGEN05 = _os.environ.get("QEC_GEN2_TC", "1") != "0"
+# Forward of quater_gen2 on the package's own tcgen05 kernel (1) or as a cuBLAS 3xTF32 GEMM (0, default).  Measured at
+# BASELINE config 2 (671 MB of output): own kernel 158 us incl. its operand prep, cuBLAS 120 us + 14 us of operand
+# launches -- the own kernel moves 336 KB through shared memory per 64 KB output tile (operand fill, three operand
+# reads, staging for the TMA store) and is bound by that; cuBLAS pairs two SMs per tile.  Step 2.524 vs 2.500 ms.
+GEN2_FORWARD_TCGEN05 = _os.environ.get("QEC_GEN2_FWD_TC", "0") != "0"
 # quater_gen1 (O <= 64) and the composition of the two Linears on the package's own FP32 kernels (1) or on cuBLAS (0)
 OWN_SMALL_LINEARS = _os.environ.get("QEC_OWN_LINEARS", "1") != "0"
 
@@ -154,11 +159,14 @@ class _TransformRoutingFused(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, W2, b2, perm, lrfs, activation, alpha, beta, num_iterations):
         T = int(num_iterations)
-        K = h.shape[1] + 1
-        W3 = 3 * K + ((-3 * K) % 16)  # tensor-core kernels need an aligned contraction length
-        A, _ = QF.split_operand(h, None, 1.0, None, True, (1, 1, 2), K, W3)
-        Bm, _ = QF.split_operand(W2, b2, 0.0, perm, True, (1, 2, 1), K, W3)
-        t_oqi = _mm(True, torch.matmul, A, Bm.t())
+        if GEN2_FORWARD_TCGEN05 and QF.gen2_fwd_supported(h.shape[0], W2.shape[0], h.shape[1]):
+            t_oqi = QF.gen2_forward(h, W2, b2, perm)  # csrc/gen2_fwd.cu: TMA + tcgen05, 3-term TF32 split
+        else:
+            K = h.shape[1] + 1
+            W3 = 3 * K + ((-3 * K) % 16)  # tensor-core kernels need an aligned contraction length
+            A, _ = QF.split_operand(h, None, 1.0, None, True, (1, 1, 2), K, W3)
+            Bm, _ = QF.split_operand(W2, b2, 0.0, perm, True, (1, 2, 1), K, W3)
+            t_oqi = _mm(True, torch.matmul, A, Bm.t())
         pose, agreement, poses_all, stats = QF.routing_fused_forward_raw(t_oqi, lrfs, activation, alpha, beta, T)
         ctx.save_for_backward(h, W2, b2, perm, t_oqi, lrfs, activation, alpha, beta, poses_all, stats)
         ctx.T = T
