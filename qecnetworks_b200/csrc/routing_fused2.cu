@@ -690,7 +690,8 @@ __device__ __forceinline__ void prefetch_walk(const Bwd2Geom& B, size_t offT_nex
 // which keeps both under the 128-register budget of two CTAs per SM.
 // Without PREFETCH (the chained backward) the pair's transforms and activations are STAGED: while slot m is
 // computed, slot m + 1's 40 bytes per thread travel global -> shared by cp.async into the reducer's scratch,
-// which is idle between two reductions (each thread reads back only what it copied itself: no barrier).
+// which is idle between two reductions (each thread reads back only what it copied itself: no barrier inside the pass,
+// one at its end -- see there).
 // One pair in flight leaves ~100 instructions between a direct load and its first use, and no registers
 // for a second pair.
 template <int T, bool FULL, bool PREFETCH>
@@ -775,6 +776,15 @@ __device__ __forceinline__ void bwd2_grad_pass(int np, const Bwd2Geom& B, const 
         w.next(B);
         if (PREFETCH) prefetch_walk<FULL>(B, offT_next, wp, sA, sB, np, m);
     }
+    // The staging area is the reducer's scratch, and the next PushReducer::reduce() parks every thread's partial sums
+    // there BEFORE its own barrier.  The float2 staging columns alias OTHER threads' partial-sum words, so a warp that
+    // ran a whole accumulation sweep ahead of a straggler (one cp.async of the straggler stuck behind a TLB miss is
+    // enough) overwrote the straggler's staged transforms: one k x 32 channels x 4 components of dL/dt garbage, about
+    // once per 1 000 launches at config 2.  Found and verified with scripts/race_hunt_bwd.py (0 deviations in 15 000
+    // launches with the barrier).  Measured alternatives: an mbarrier guard (arrive here, wait in reduce()): the same
+    // +13 us per backward, more live registers; staging word by word into the thread's OWN partial-sum words (no
+    // synchronisation at all): correct, but ten 4-byte cp.async + LDS per slot instead of five: +50 us.
+    if (STAGE) __syncthreads();
 }
 
 // ---- sweep that completes level TT (u^TT known) and accumulates level TT-1 (chain only)
