@@ -291,8 +291,24 @@ def kernel_work(name, dims, T):
     if name == "qec_gen2_bwd":
         # backward of quater_gen2 (two products over the transform gradient g [M, N], both outputs tiny): the
         # algorithmic minimum reads g once; this implementation reads it once per product (tcgen05 tf32 x3, TMA-fed)
+        # FLOP: 0 on the FP32 roof -- the products run on the tensor cores (3 x 2 x 2MN(Kc+1) TF32 FLOP = 0.5 % of the
+        # tensor peak over the kernel's duration): the kernel is HBM-bound by construction
         M, N, Kc = dims[:3]
-        return 4 * M * N + 8 * (M + N) * Kc, 2 * 2 * M * N * (Kc + 1), 8 * M * N + 2 * 24 * 48 * 4 * (M + N)
+        return 4 * M * N + 8 * (M + N) * Kc, 0, 8 * M * N + 2 * 24 * 48 * 4 * (M + N)
+    if name == "qec_gen2_fwd":
+        # forward of quater_gen2 on the tensor cores: bound by writing t [M, N]
+        M, N, Kc = dims[:3]
+        return 4 * M * N + 4 * (M + N) * (Kc + 1), 0, 4 * M * N + 3 * 8 * 64 * (M + N)
+    if name in ("qec_linear_fwd", "qec_linear_bwd"):
+        M, C, O = dims[:3]
+        if name == "qec_linear_fwd":
+            return 4 * (M * (C + O) + O * C), 2 * M * C * O, 4 * (M * (C + O) + O * C)
+        nblk = (M + 63) // 64
+        return 4 * (M * (2 * C + O) + 2 * O * C), 4 * M * C * O, 4 * (M * (2 * C + O) + 2 * O * C + 2 * nblk * O * (C + 1))
+    if name in ("qec_compose_fwd", "qec_compose_bwd"):
+        R, O, C = dims[:3]
+        by = 4 * (R * O + O * C + R * C + R + O)
+        return (by, 2 * R * O * (C + 1), by) if name == "qec_compose_fwd" else (by + 4 * R * O, 4 * R * O * (C + 1), by + 4 * R * O)
     if name in ("qec_lrf_mean_fwd", "qec_lrf_mean_bwd"):
         BP, K, I = dims[:3]
         Nn, Nm = BP * K * I, BP * I

@@ -118,11 +118,22 @@ def test_direct_gradient_placement_matches_accumulating_bucket():
             buck.check_views()   # every .grad aliases its slice of the flat buffer
             grads.append(buck.flat.clone())
         scale = float(grads[1].abs().max())
-        err = float((grads[0] - grads[1]).abs().max()) / scale
-        print("direct margin grads step=%d err=%.2e tol=5.00e-05" % (step, err))
-        # same kernels either way; what differs run to run is the order of the FP32 atomics (dL/dlrfs of pool2 feeds
-        # the whole pool1 backward): ~1e-5 of the largest entry.  A lost or doubled gradient would be O(1).
-        assert err < 5e-5, err
+        # same kernels either way; what differs run to run is the order of the FP32 atomics: dL/dlrfs of pool2 feeds the
+        # whole pool1 backward (~1e-6 of the largest entry), and dL/d(alpha, beta) are themselves sums accumulated with
+        # atomics -- pool2.beta a near-cancelling one that moves by up to 1e-4 of the largest entry from run to run
+        # (scripts/flaky_hunt.py).  A lost or doubled gradient would be O(1) of the tensor's own size.
+        off = 0
+        for p in buck_a.params:
+            n = p.numel()
+            da, db = grads[0][off:off + n], grads[1][off:off + n]
+            off += n
+            atomic_sum = n == 1   # alpha / beta
+            tol = 1e-3 if atomic_sum else 5e-5
+            err = float((da - db).abs().max()) / scale
+            print("direct margin grads step=%d numel=%d err=%.2e tol=%.2e" % (step, n, err, tol))
+            assert err < tol, (n, err)
+            own = float(db.abs().max())
+            assert own > 0.0 and float((da - db).abs().max()) < 0.5 * own + 1e-4 * scale, (n, own)   # present, not doubled
         opt_a.step()
         opt_b.step()
         assert float(buck_a.flat.abs().max()) == 0.0 and all(p.grad is None for p in net_a.parameters())

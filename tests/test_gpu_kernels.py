@@ -921,3 +921,36 @@ def test_gen2_forward_tcgen05(M, N, Kc, use_perm):
     print("gen2fwd margin t M=%d N=%d Kc=%d err=%.2e tol=2.00e-06" % (M, N, Kc, e))
     assert e < 2e-6, e
     assert not QF.gen2_fwd_supported(100, 128, 40) and not QF.gen2_fwd_supported(128, 128, 64)
+
+
+def test_routing_fused_backward_bit_reproducible():
+    """dL/dt of the cluster-resident backward has no atomics on its path: the same launch must give the same bits every
+    time, also with another kernel (qec_gen2_bwd: different shared-memory carve-out, cold L2 / TLB) running between
+    the repetitions.  This is the regression guard of a race found in round 2 (operands staged in the reducer's
+    scratch were overwritten by a warp a whole sweep ahead: one k x 32 channels x 4 components wrong about once per
+    1 000 launches; scripts/race_hunt_bwd.py is the long form of this test)."""
+    from qecnetworks_b200 import functional as QF
+
+    dev = cuda()
+    B, P, K, I, O, T = 2, 1, 256, 128, 40, 3
+    g = torch.Generator().manual_seed(3)
+    lrfs = clustered((B, P, K, I), g, spread=0.3).to(dev)
+    act = (torch.rand(B, P, K * I, generator=g) * 0.5 + 0.4).to(dev)
+    tb = torch.randn(1, O, 4, 1, generator=g)
+    t = (tb + 0.25 * torch.randn(B * P * K, O, 4, I, generator=g)).reshape(B * P * K, 4 * I * O).to(dev)
+    alpha, beta = torch.ones(1, device=dev), torch.ones(1, device=dev)
+    Gp = torch.randn(B, P, O, 4, generator=g).to(dev)
+    Ga = torch.randn(B, P, O, generator=g).to(dev)
+    h = torch.randn(B * P * K, O, generator=g).to(dev)
+    W2 = (torch.randn(4 * I * O, O, generator=g) / 6).to(dev)
+    perm = torch.randperm(4 * I * O, generator=g).to(dev)
+    pose, agr, poses_all, stats = QF.routing_fused_forward_raw(t, lrfs, act, alpha, beta, T)
+    ref = ref2 = None
+    for r in range(2000):
+        gt, gl, ga, _ = QF.routing_fused_backward_raw(t, lrfs, act, alpha, beta, poses_all, stats, Gp, Ga, T, True, True)
+        outs = QF.gen2_backward(gt, h, W2, perm)
+        if ref is None:
+            ref, ref2 = gt.clone(), [x.clone() for x in outs]
+            continue
+        assert torch.equal(gt, ref), "dL/dt differs in repetition %d (%d elements)" % (r, int((gt != ref).sum()))
+        assert all(torch.equal(x, y) for x, y in zip(outs, ref2)), "qec_gen2_bwd differs in repetition %d" % r
