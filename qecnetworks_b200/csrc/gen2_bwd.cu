@@ -47,7 +47,10 @@ namespace g2 {
 constexpr int kCvtThreads = 128;  // warps 0-3: split the tile of g, finally drain the accumulator
 constexpr int kThreads = 192;     // + warp 4: MMA issuer / tensor-memory allocator, warp 5: TMA producer
 constexpr int kNB = 48;           // padded width of the small operand (Kc + 1 <= 48): the MMA's N
-constexpr int kStages = 5;
+#ifndef QEC_G2_STAGES
+#define QEC_G2_STAGES 5
+#endif
+constexpr int kStages = QEC_G2_STAGES;  // ring depth: 5 x 44 KB fill the SM; fewer leave room for a co-resident kernel
 constexpr int kTileBytes = 16 * 1024;           // a chunk of g: [128 x 32] (mode 0) or [32 x 128] (mode 1) floats
 constexpr int kSmallBytes = kNB * 32 * 4;       // the matching chunk of the small operand: 48 rows x 32 k, K-major
 constexpr int kStageBytes = 2 * kTileBytes + 2 * kSmallBytes;  // g hi, g lo, small hi, small lo

@@ -23,6 +23,8 @@ t = (tb + 0.25 * torch.randn(B * P * K, O, 4, I, generator=g)).reshape(B * P * K
 alpha = torch.ones(1, device=dev); beta = torch.ones(1, device=dev)
 Gp = torch.randn(B, P, O, 4, generator=g).to(dev); Ga = torch.randn(B, P, O, generator=g).to(dev)
 pose, agr, poses_all, stats = QF.routing_fused_forward_raw(t, lrfs, act, alpha, beta, T)
+fwd_ref = [x.clone() for x in (pose, agr, poses_all, stats)]
+bad_fwd = 0
 h = torch.randn(B * P * K, O, generator=g).to(dev)
 W2 = (torch.randn(4 * I * O, O, generator=g) / 6).to(dev)
 perm = torch.randperm(4 * I * O, generator=g).to(dev)
@@ -31,6 +33,10 @@ bad2 = 0
 ref = None
 bad = 0
 for r in range(reps):
+    fw = QF.routing_fused_forward_raw(t, lrfs, act, alpha, beta, T)   # the forward has no atomics at all
+    if not all(torch.equal(x, y) for x, y in zip(fw, fwd_ref)):
+        bad_fwd += 1
+        print("rep %d: forward outputs differ: %s" % (r, [int((x != y).sum()) for x, y in zip(fw, fwd_ref)]))
     gt, gl, ga, gab = QF.routing_fused_backward_raw(t, lrfs, act, alpha, beta, poses_all, stats, Gp, Ga, T, True, True, split=split)
     if not split and QF.gen2_bwd_supported(gt.shape[0], gt.shape[1], O):
         outs = QF.gen2_backward(gt, h, W2, perm)   # deterministic by design: any deviation with an identical g is a race
@@ -68,4 +74,4 @@ for r in range(reps):
     le = float((gl - ref[1]).abs().max() / ref[1].abs().max()); ae = float((ga - ref[2]).abs().max() / ref[2].abs().max())
     if le > 1e-4 or ae > 1e-4:
         print("rep %d: dL/dlrfs rel %.2e, dL/dact rel %.2e" % (r, le, ae))
-print("reps %d, deviating dL/dt: %d, deviating gen2_bwd outputs: %d" % (reps, bad, bad2))
+print("reps %d, deviating forward: %d, deviating dL/dt: %d, deviating gen2_bwd outputs: %d" % (reps, bad_fwd, bad, bad2))
