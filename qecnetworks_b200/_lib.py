@@ -18,8 +18,8 @@ _D = ctypes.c_double
 # name -> (argtypes, kernels launched per call)
 SIGNATURES = {
     "qec_b200_version": ([], 0),
-    # (mean LRF + point rotation: one launch for K <= 32, mean and rotation separately for the tile kernels)
-    "qec_lrf_mean_fwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _P], lambda a: 1 if (a[6] <= 32 or not a[4]) else 2),
+    # (mean LRF + point rotation: one launch for K <= 32 and for the tile kernel (I >= 32); two otherwise)
+    "qec_lrf_mean_fwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _P], lambda a: 1 if (a[6] <= 32 or a[7] >= 32 or not a[4]) else 2),
     "qec_lrf_mean_bwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P], 1),
     "qec_votes_fwd": ([_P, _P, _P, _I, _I, _I, _I, _P], 1),
     "qec_votes_bwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _P], 1),

@@ -136,8 +136,9 @@ constexpr int kTW = 16;  // warps per CTA = slices of k
 
 __global__ void __launch_bounds__(kTW * 32)
     lrf_mean_fwd_tile_kernel(const float* __restrict__ lrfs, const float* __restrict__ act, float* __restrict__ mean,
-                             int K, int I) {
+                             int K, int I, const float* __restrict__ points, float* __restrict__ xrot) {
     __shared__ float part[kTW][11][32];
+    __shared__ float ms[4][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tiles = (I + 31) / 32;
     const long long bp = blockIdx.x / tiles;
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(kTW * 32)
     float acc[11];  // M (10), number of active neighbours
     zero_acc(acc);
     if (live) {
-#pragma unroll 4
+#pragma unroll 8  // 16 neighbours per warp at K = 256: two rounds of eight loads in flight
         for (int k = warp; k < K; k += kTW) {
             const size_t e = ((size_t)bp * K + k) * I + i;
             const Quat q = ldq_nc(lrfs + e * 4);
@@ -169,6 +170,21 @@ __global__ void __launch_bounds__(kTW * 32)
         Quat p = qfix(top_eigvec_psd(m, WarpDone()));  // (1/K) sum q q^T is positive semi-definite
         if (!(acc[10] > 0.f)) p = qmake(0.f, 0.f, 0.f, 0.f);
         if (live) stq(mean + ((size_t)bp * I + i) * 4, p);
+        ms[0][lane] = p.w; ms[1][lane] = p.x; ms[2][lane] = p.y; ms[3][lane] = p.z;
+    }
+    if (xrot == nullptr) return;
+    // the rotation of the patch's points into the mean frame (the qrotv at the top of get_votes) in the same launch:
+    // every warp rotates its slice of k for the tile's 32 channels
+    __syncthreads();
+    if (!live) return;
+    const Quat cj = qconj(qmake(ms[0][lane], ms[1][lane], ms[2][lane], ms[3][lane]));
+#pragma unroll 4
+    for (int k = warp; k < K; k += kTW) {
+        const size_t bpk = (size_t)bp * K + k;
+        const float* pp = points + bpk * 3;
+        const Vec3 x = qrotv(cj, vmake(__ldg(pp), __ldg(pp + 1), __ldg(pp + 2)));
+        float* o = xrot + (bpk * I + i) * 3;
+        o[0] = x.x; o[1] = x.y; o[2] = x.z;
     }
 }
 
@@ -189,7 +205,7 @@ __global__ void __launch_bounds__(kTW * 32)
     float acc[14];  // g_conj (4), M (10)
     zero_acc(acc);
     if (live) {
-#pragma unroll 2
+#pragma unroll 4
         for (int k = warp; k < K; k += kTW) {
             const size_t bpk = (size_t)bp * K + k;
             const size_t e = bpk * I + i;
@@ -233,6 +249,7 @@ __global__ void __launch_bounds__(kTW * 32)
     __syncthreads();
     if (!live) return;
     const Quat u = qmake(us[0][lane], us[1][lane], us[2][lane], us[3][lane]);
+#pragma unroll 8
     for (int k = warp; k < K; k += kTW) {
         const size_t e = ((size_t)bp * K + k) * I + i;
         const Quat q = ldq_nc(lrfs + e * 4);
@@ -263,7 +280,8 @@ extern "C" int qec_lrf_mean_fwd(const float* lrfs, const float* act, const float
         return launch_status();  // rotation done in the same launch
     } else if (I >= 32) {
         const long long blocks = (long long)BP * ((I + 31) / 32);
-        lrf_mean_fwd_tile_kernel<<<(unsigned)blocks, kTW * 32, 0, st>>>(lrfs, act, mean, K, I);
+        lrf_mean_fwd_tile_kernel<<<(unsigned)blocks, kTW * 32, 0, st>>>(lrfs, act, mean, K, I, points, xrot);
+        return launch_status();  // rotation done in the same launch
     } else {
         const long long blocks = (Ncap * 32 + kLT - 1) / kLT;
         lrf_mean_fwd_kernel<32><<<(unsigned)blocks, kLT, 0, st>>>(lrfs, act, mean, Ncap, K, I);
