@@ -143,6 +143,7 @@ class Routing(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, votes, activation, alpha, beta, num_iterations):
+        ctx.set_materialize_grads(False)  # an unused output arrives as None, not as a zero tensor autograd has to fill
         B, P, O, J, _ = votes.shape
         votes = _check(votes, "votes", (B, P, O, J, 4))
         activation = _check(activation, "activation", (B, P, J))
@@ -243,6 +244,7 @@ class RoutingFused(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, t_oqi, lrfs, activation, alpha, beta, num_iterations):
+        ctx.set_materialize_grads(False)  # an unused output arrives as None, not as a zero tensor autograd has to fill
         T = int(num_iterations)
         pose, agreement, poses_all, stats = routing_fused_forward_raw(t_oqi, lrfs, activation, alpha, beta, T)
         ctx.save_for_backward(t_oqi, lrfs, activation, alpha, beta, poses_all, stats)
@@ -509,6 +511,7 @@ class RoutingSmall(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xrot, lrfs, activation, Wc, bc, alpha, beta, num_iterations, keep):
+        ctx.set_materialize_grads(False)  # an unused output arrives as None, not as a zero tensor autograd has to fill
         # keep: a backward may follow (decided by the caller: inside forward() the grad mode is always off, and
         # needs_input_grad reflects requires_grad of the inputs even under no_grad)
         saved = bool(keep)

@@ -158,6 +158,7 @@ class _TransformRoutingFused(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, h, W2, b2, perm, lrfs, activation, alpha, beta, num_iterations):
+        ctx.set_materialize_grads(False)  # an unused output (the pose under a pure classification loss) arrives as None
         T = int(num_iterations)
         if GEN2_FORWARD_TCGEN05 and QF.gen2_fwd_supported(h.shape[0], W2.shape[0], h.shape[1]):
             t_oqi = QF.gen2_forward(h, W2, b2, perm)  # csrc/gen2_fwd.cu: TMA + tcgen05, 3-term TF32 split
