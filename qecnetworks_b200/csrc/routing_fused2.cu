@@ -274,6 +274,32 @@ struct PairGeom {
 };
 
 // issue the asynchronous copy of capsule (bp, o)'s transforms into the vote slots, one commit group per slot
+// Raw transforms travel global -> shared as 8-byte cp.async into the two halves of 16-byte slots: with every lane writing
+// the same half, a warp's 32 writes fall on half of the banks (2-way conflict: 7.5 M extra wavefronts per forward, 11 M
+// per backward at config 2).  QEC_RAW_SWZ=1 exchanges the halves for every other group of eight lanes (bit 3 of the
+// thread index: constant per thread, since slots advance by the CTA size), so that sixteen lanes cover all 32 banks;
+// sweep 0 reads the raw slot back as 4 x LDS.64 from the exchanged addresses (same wavefronts as 2 x LDS.128) and
+// stores the votes in the regular layout.
+#ifndef QEC_RAW_SWZ
+#define QEC_RAW_SWZ 0
+#endif
+__device__ __forceinline__ int raw_half() { return QEC_RAW_SWZ ? (int)((threadIdx.x >> 3) & 1u) * 2 : 0; }
+__device__ __forceinline__ Quat2 lds_pair_raw(const float4* sA, const float4* sB, int ps) {
+#if QEC_RAW_SWZ
+    const int h = raw_half();
+    const float* a = reinterpret_cast<const float*>(sA + ps);
+    const float* b = reinterpret_cast<const float*>(sB + ps);
+    Quat2 v;
+    v.w = lds_f2(reinterpret_cast<const float2*>(a + h));
+    v.x = lds_f2(reinterpret_cast<const float2*>(a + 2 - h));
+    v.y = lds_f2(reinterpret_cast<const float2*>(b + h));
+    v.z = lds_f2(reinterpret_cast<const float2*>(b + 2 - h));
+    return v;
+#else
+    return lds_pair(sA, sB, ps);
+#endif
+}
+
 template <bool FULL>
 __device__ __forceinline__ void prefetch_slot(const PairGeom& G, const float* tcap, float4* sA, float4* sB, int m) {
     const int ps = threadIdx.x + m * kPT;
@@ -281,10 +307,11 @@ __device__ __forceinline__ void prefetch_slot(const PairGeom& G, const float* tc
         const float* tp = tcap + G.off[m];
         float* a = reinterpret_cast<float*>(sA + ps);
         float* b = reinterpret_cast<float*>(sB + ps);
-        cp_async8(a, tp);
-        cp_async8(a + 2, tp + G.I);
-        cp_async8(b, tp + 2 * G.I);
-        cp_async8(b + 2, tp + 3 * G.I);
+        const int h = raw_half();
+        cp_async8(a + h, tp);
+        cp_async8(a + 2 - h, tp + G.I);
+        cp_async8(b + h, tp + 2 * G.I);
+        cp_async8(b + 2 - h, tp + 3 * G.I);
     }
     cp_async_commit();
 }
@@ -382,7 +409,7 @@ __global__ void __launch_bounds__(kPT, kCtasPerSM)
                 acc_rank1_2(m2, a, v);
                 comp = add2(comp, add2(add2(v.w, v.x), add2(v.y, v.z)));
             };
-            auto gen = [&](int m, const Quat2& lrf, f2 a) { gen_t(m, lrf, a, lds_pair(sA, sB, threadIdx.x + m * kPT)); };
+            auto gen = [&](int m, const Quat2& lrf, f2 a) { gen_t(m, lrf, a, lds_pair_raw(sA, sB, threadIdx.x + m * kPT)); };
             auto ldl = [&](int m, Quat2& lrf, f2& a) {  // the pair's LRFs and activations (L2-resident: shared by all O)
                 const int ps = threadIdx.x + m * kPT;
                 if (live(m)) {
@@ -399,12 +426,12 @@ __global__ void __launch_bounds__(kPT, kCtasPerSM)
             // the transforms of slot M+1 leave shared memory before slot M is generated and stored
             Quat2 tr[2];
             wait_slot<0>();
-            if (live(0)) tr[0] = lds_pair(sA, sB, threadIdx.x);
+            if (live(0)) tr[0] = lds_pair_raw(sA, sB, threadIdx.x);
 #define QEC_GEN_SLOT(M)                                                                        \
     if ((M) + 2 < kPairs) ldl((M) + 2, lr[((M) + 2) % 3], av[((M) + 2) % 3]);                  \
     if ((M) + 1 < kPairs) {                                                                    \
         wait_slot<((M) + 1 < kPairs ? (M) + 1 : 0)>();                                         \
-        if (live((M) + 1)) tr[((M) + 1) & 1] = lds_pair(sA, sB, threadIdx.x + ((M) + 1) * kPT); \
+        if (live((M) + 1)) tr[((M) + 1) & 1] = lds_pair_raw(sA, sB, threadIdx.x + ((M) + 1) * kPT); \
     }                                                                                          \
     if (live(M)) gen_t((M), lr[(M) % 3], av[(M) % 3], tr[(M) & 1]);
 #else
@@ -676,10 +703,11 @@ __device__ __forceinline__ void prefetch_walk(const Bwd2Geom& B, size_t offT_nex
         const float* tp = B.t_oqi + (offT_next + (size_t)w.off);
         float* a = reinterpret_cast<float*>(sA + ps);
         float* b = reinterpret_cast<float*>(sB + ps);
-        cp_async8(a, tp);
-        cp_async8(a + 2, tp + B.I);
-        cp_async8(b, tp + 2 * B.I);
-        cp_async8(b + 2, tp + 3 * B.I);
+        const int h = raw_half();
+        cp_async8(a + h, tp);
+        cp_async8(a + 2 - h, tp + B.I);
+        cp_async8(b + h, tp + 2 * B.I);
+        cp_async8(b + 2 - h, tp + 3 * B.I);
     }
     cp_async_commit();
     w.next(B);
@@ -932,19 +960,19 @@ __device__ __forceinline__ void bwd2_sweep0(int np, const Bwd2Geom& B, const Bwd
 #if (QEC_SWP & 16)
     Quat2 tr[2];  // the transforms of slot M+1 leave shared memory before slot M is generated and stored
     wait_slot<0>();
-    if (FULL || threadIdx.x < np) tr[0] = lds_pair(sA, sB, threadIdx.x);
+    if (FULL || threadIdx.x < np) tr[0] = lds_pair_raw(sA, sB, threadIdx.x);
 #define QEC_GEN_SLOT(M)                                                                              \
     if ((M) + 2 < kPairs) ldl((M) + 2, lr[((M) + 2) % 3], av[((M) + 2) % 3]);                        \
     if ((M) + 1 < kPairs) {                                                                          \
         wait_slot<((M) + 1 < kPairs ? (M) + 1 : 0)>();                                               \
-        if (FULL || (threadIdx.x + ((M) + 1) * kPT < np)) tr[((M) + 1) & 1] = lds_pair(sA, sB, threadIdx.x + ((M) + 1) * kPT); \
+        if (FULL || (threadIdx.x + ((M) + 1) * kPT < np)) tr[((M) + 1) & 1] = lds_pair_raw(sA, sB, threadIdx.x + ((M) + 1) * kPT); \
     }                                                                                                \
     if (FULL || (threadIdx.x + (M) * kPT < np)) gen_t((M), lr[(M) % 3], av[(M) % 3], tr[(M) & 1]);
 #else
 #define QEC_GEN_SLOT(M)                                                       \
     if ((M) + 2 < kPairs) ldl((M) + 2, lr[((M) + 2) % 3], av[((M) + 2) % 3]); \
     wait_slot<(M)>();                                                         \
-    if (FULL || (threadIdx.x + (M) * kPT < np)) gen_t((M), lr[(M) % 3], av[(M) % 3], lds_pair(sA, sB, threadIdx.x + (M) * kPT));
+    if (FULL || (threadIdx.x + (M) * kPT < np)) gen_t((M), lr[(M) % 3], av[(M) % 3], lds_pair_raw(sA, sB, threadIdx.x + (M) * kPT));
 #endif
     QEC_GEN_SLOT(0) QEC_GEN_SLOT(1) QEC_GEN_SLOT(2) QEC_GEN_SLOT(3)
     QEC_GEN_SLOT(4) QEC_GEN_SLOT(5) QEC_GEN_SLOT(6) QEC_GEN_SLOT(7)
