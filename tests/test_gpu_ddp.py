@@ -10,7 +10,7 @@ import torch.multiprocessing as mp
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, direct=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     import qecnetworks_b200 as qb
@@ -22,7 +22,8 @@ def _worker(rank, world, port, out):
     torch.manual_seed(7)
     net = qb.QecNet(2048, 16, 10, 3).to(dev)
     ddp.broadcast_parameters(net, 0)
-    bucket = ddp.FlatGradBucket(net.parameters(), early=list(net.pool2.parameters()))  # overlapped slice
+    # overlapped slice; direct: the backward kernels write into the flat buffer themselves (what bench.py runs)
+    bucket = ddp.FlatGradBucket(net.parameters(), early=list(net.pool2.parameters()), direct=direct)
     B = 4
     points, lrfs, act, labels = [t.to(dev) for t in synthetic_batch(B * world, ncls=10, seed=11)]
     lo, hi = ddp.shard_batch(B * world, rank, world)
@@ -70,6 +71,17 @@ def test_ddp_gradients_match_global_batch():
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(2, 29731, out), nprocs=2, join=True)
+    assert out[0] < 1e-4 and out[1] < 1e-4, dict(out)
+
+
+def test_ddp_direct_gradient_placement_match_global_batch():
+    """the same with FlatGradBucket(direct=True): parameter gradients written by the kernels straight into the flat
+    buffer, the early slice all-reduced from the post-accumulate hooks, FlatAdam re-arming the slices"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, 29741, out, True), nprocs=2, join=True)
     assert out[0] < 1e-4 and out[1] < 1e-4, dict(out)
 
 
