@@ -5,6 +5,8 @@ import torch
 import qecnetworks_b200 as qb
 from qecnetworks_b200 import _lib
 from oracle import qec_oracle as orc
+if os.environ.get("QEC_LIB"):  # a timing variant
+    _lib.LIB_PATH = os.path.abspath(os.environ["QEC_LIB"])
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 m = qb.QecModule(1, 128, 3, 9, 256).to(dev)
