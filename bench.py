@@ -421,7 +421,9 @@ def run_b200(a):
     ddp.broadcast_parameters(net, 0)
     # pool2's gradients (90 % of the bytes) are all-reduced while the pool1 backward still runs
     # direct: the backward kernels write the parameter gradients straight into the flat buffer (no per-parameter add)
-    bucket = ddp.FlatGradBucket(net.parameters(), early=list(net.pool2.parameters()), direct=True)
+    # (QEC_DDP_EARLY=0: one all-reduce of the whole buffer after the backward instead of the overlapped early slice)
+    early = list(net.pool2.parameters()) if os.environ.get("QEC_DDP_EARLY", "1") != "0" else None
+    bucket = ddp.FlatGradBucket(net.parameters(), early=early, direct=True)
     # train_cls.py:44-51 (Adam, default betas/eps): one launch over the flat buffers, which also applies the
     # 1/world of the all-reduce and re-zeroes the gradient buffer (tests/test_gpu_adam.py: == torch.optim.Adam)
     opt = ddp.FlatAdam(bucket, lr=1e-3)

@@ -94,7 +94,9 @@ class FlatGradBucket:
         self._seen = 0
         self._work = None
         self._group = group  # fixed at construction: the hooks and all_reduce_mean() use the same one
-        self.overlap = True  # set to False for a backward pass that must not touch the network (no all_reduce_mean after it)
+        # set to False for a backward pass that must not touch the network (no all_reduce_mean after it);
+        # QEC_DDP_OVERLAP=0 starts with it off (A/B measurements of the overlap)
+        self.overlap = os.environ.get("QEC_DDP_OVERLAP", "1") != "0"
         for p in self.early:
             p.register_post_accumulate_grad_hook(self._on_early_grad)
 
