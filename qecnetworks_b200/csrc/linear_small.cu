@@ -62,19 +62,25 @@ __device__ __forceinline__ void load_chunk_async(float* dst, const float* __rest
     }
 }
 
-// y[m][o] = b[o] + sum_c x[m][c] W[o][c].  Thread (rg = tid / 8, og = tid % 8): rows rg, rg + 32; outputs og + 8 j.
+// y[m][o] = b[o] + sum_c x[m][c] W[o][c].  The 256 threads are four groups of 64; group kg takes the float4 columns
+// c4 = kg, kg + 4, ... of every chunk (a 4-way split of the contraction), and inside a group thread (rg = t / 8, og = t % 8)
+// owns the rows rg + 8 i (i < 8) x the outputs og + 8 j: 8 + NJ shared-memory loads per 32 NJ FMA.  (The first version
+// gave every thread 2 rows x NJ outputs of the whole contraction: 2 + NJ loads per 8 NJ FMA -- bound by shared-memory
+// wavefronts, 18 us at [8192 x 384] -> 40.)  The four partial sums meet in shared memory at the end, in a fixed order.
 template <int NJ>
 __global__ void __launch_bounds__(kThreads)
     linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b,
                       float* __restrict__ y, int M, int C, int O) {
     extern __shared__ __align__(16) float sm[];
     constexpr int kBuf = (8 * NJ + kRows) * kPitch;  // one stage: W chunk [8 NJ][kPitch] + x chunk [kRows][kPitch]
-    const int tid = threadIdx.x, og = tid & 7, rg = tid >> 3;
+    const int tid = threadIdx.x, kg = tid >> 6, t64 = tid & 63, og = t64 & 7, rg = t64 >> 3;
     const int m0 = blockIdx.x * kRows;
     const int nchunks = (C + kChunk - 1) / kChunk;
-    float acc[2][NJ];
+    float acc[8][NJ];
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) acc[0][j] = acc[1][j] = 0.f;
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
     auto issue = [&](int k) {
         float* ws = sm + (k & 1) * kBuf;
         load_chunk_async(ws, W, 0, 8 * NJ, O, C, k * kChunk, tid);
@@ -93,28 +99,34 @@ __global__ void __launch_bounds__(kThreads)
         const float* ws = sm + (k & 1) * kBuf;
         const float* xs = ws + 8 * NJ * kPitch;
         const int n4 = (min(kChunk, C - k * kChunk) + 3) / 4;
-#pragma unroll 2
-        for (int c4 = 0; c4 < n4; ++c4) {
-            const float4 x0 = *reinterpret_cast<const float4*>(xs + rg * kPitch + 4 * c4);
-            const float4 x1 = *reinterpret_cast<const float4*>(xs + (rg + 32) * kPitch + 4 * c4);
+        for (int c4 = kg; c4 < n4; c4 += 4) {
+            float4 w[NJ];
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const float4 w = *reinterpret_cast<const float4*>(ws + (og + 8 * j) * kPitch + 4 * c4);
-                acc[0][j] = dot4(x0, w, acc[0][j]);
-                acc[1][j] = dot4(x1, w, acc[1][j]);
+            for (int j = 0; j < NJ; ++j) w[j] = *reinterpret_cast<const float4*>(ws + (og + 8 * j) * kPitch + 4 * c4);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 xv = *reinterpret_cast<const float4*>(xs + (rg + 8 * i) * kPitch + 4 * c4);
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) acc[i][j] = dot4(xv, w[j], acc[i][j]);
             }
         }
         __syncthreads();
     }
+    // the four groups' partial sums: red[(kg * 8 NJ + e) * 64 + t64], e = i * NJ + j (stride 64: conflict-free), added in
+    // group order by the thread that writes the output
+    float* red = sm;  // 4 * 8 NJ * 64 floats <= two stages (every stage was released by the last barrier)
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int m = m0 + rg + 32 * i;
-        if (m >= M) continue;
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            const int o = og + 8 * j;
-            if (o < O) y[(size_t)m * O + o] = acc[i][j] + __ldg(b + o);
-        }
+        for (int j = 0; j < NJ; ++j) red[(kg * 8 * NJ + i * NJ + j) * 64 + t64] = acc[i][j];
+    __syncthreads();
+    for (int q = tid; q < 8 * NJ * 64; q += kThreads) {
+        const int e = q >> 6, t = q & 63;
+        const int i = e / NJ, j = e - i * NJ;
+        const int m = m0 + (t >> 3) + 8 * i, o = (t & 7) + 8 * j;
+        if (m >= M || o >= O) continue;
+        const float s = ((red[q] + red[q + 8 * NJ * 64]) + red[q + 2 * 8 * NJ * 64]) + red[q + 3 * 8 * NJ * 64];
+        y[(size_t)m * O + o] = s + __ldg(b + o);
     }
 }
 
