@@ -1266,7 +1266,8 @@ extern "C" int qec_routing_fused_set_wide(int mode) {
 }
 
 // Third generation (routing_fused3.cu: two capsules in flight per cluster, dedicated solver warp).  Bit 0: forward,
-// bit 1: backward.  Initial value from the environment (QEC_FUSED_PP, default 3 = both).
+// bit 1: reserved for a backward (none was built).  Initial value from the environment (QEC_FUSED_PP), default
+// QEC_PP_DEFAULT = 0: off (measured slower than the second generation).
 extern "C" int qec_routing_fused_pp_supported(int K, int I, int O, int T);
 extern "C" int qec_routing_fused_pp_fwd(const float* t_oqi, const float* lrfs, const float* act, const float* alpha,
                                         const float* beta, float* pose, float* agreement, float* poses_all, float* stats,
